@@ -1,0 +1,66 @@
+// drl_pack.cuh -- canonical (state_dict order) <-> packed (kernel) parameter index map, and the
+// layout of the caller-owned update workspace.
+#pragma once
+#include "drl_common.cuh"
+
+namespace drl {
+
+int check_net(const drl_net_t* net);
+
+// Store canonical parameter `i` (value v) at its packed position(s).  The H x H matrices are kept
+// twice: W2T for the forward pass, W2P for the backward pass.
+template <int O, int A>
+__device__ __forceinline__ void packed_store(float* __restrict__ packed, int i, float v) {
+    using P = Packed<O, A>;
+    const int net = i >= P::C_ACTOR ? 1 : 0;
+    int r = i - net * P::C_ACTOR;
+    if (r < H * O) {
+        const int o = r / O, k = r % O;
+        packed[P::W1T + (net * O + k) * H + perm_pos(o)] = v;
+        return;
+    }
+    r -= H * O;
+    if (r < H) { packed[P::B1 + net * H + perm_pos(r)] = v; return; }
+    r -= H;
+    if (r < H * H) {
+        const int o = r / H, k = r % H;
+        packed[P::W2T + (net * H + k) * H + perm_pos(o)] = v;
+        packed[P::W2P + (net * H + o) * H + perm_pos(k)] = v;
+        return;
+    }
+    r -= H * H;
+    if (r < H) { packed[P::B2 + net * H + perm_pos(r)] = v; return; }
+    r -= H;
+    const int nout = net == 0 ? A : 1;
+    if (r < nout * H) {
+        const int a = r / H, k = r % H;
+        packed[P::W4 + (net * A + a) * H + perm_pos(k)] = v;
+        return;
+    }
+    r -= nout * H;
+    packed[P::B4 + net * A + r] = v;
+}
+
+// ---- update workspace (caller-owned, zero-initialised once) ----
+constexpr int MAX_GRAD_CTAS = 160;   // >= SM count (148); the grad kernel runs one persistent CTA per SM
+constexpr int MAX_MINIBATCHES = 16;
+constexpr int STAT_PARTS = 64;       // partial-sum CTAs per minibatch in drl_adv_stats
+constexpr int LOSS_TERMS = 8;
+
+struct WorkspaceLayout {
+    size_t counters, stat_partials, loss_partials, grad_partials, total;
+    int ppad;
+};
+inline WorkspaceLayout workspace_layout(int64_t P) {
+    WorkspaceLayout w;
+    w.ppad = (int)((P + 3) / 4 * 4);
+    w.counters = 0;
+    w.stat_partials = 64;
+    w.loss_partials = w.stat_partials + sizeof(double) * MAX_MINIBATCHES * STAT_PARTS * 2;
+    w.grad_partials = w.loss_partials + sizeof(float) * MAX_GRAD_CTAS * LOSS_TERMS;
+    w.total = w.grad_partials + sizeof(float) * (size_t)MAX_GRAD_CTAS * w.ppad;
+    return w;
+}
+inline size_t workspace_bytes_for(int64_t P) { return workspace_layout(P).total; }
+
+}  // namespace drl

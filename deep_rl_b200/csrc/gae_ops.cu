@@ -1,0 +1,203 @@
+// gae_ops.cu -- GAE/returns reverse-time scan (deep_rl/ppo.py:144-151), minibatch permutation
+// (ppo.py:155) and per-minibatch advantage statistics (ppo.py:169).  All HBM-bound, coalesced SoA.
+#include "drl_pack.cuh"
+
+namespace drl {
+
+// ---------------------------------------------------------------------------------------------
+// GAE: one thread per env walks t = T-1 .. 0; lanes of a warp are 32 consecutive envs, so every
+// load/store is a fully coalesced 128-byte (f32) or 32-byte (u8) row segment.  The arithmetic keeps
+// the reference's grouping and fp32 rounding (-fmad=false: nothing below is contracted):
+//     adv[t] = rew[t+1] + gamma*(1 - done[t+1]) * (val[t+1] + lambda*last) - val[t]
+// Optionally packs the per-sample record the update kernels gather: one 32-byte (O<=4) or 64-byte
+// sector-aligned row {obs.., logp, adv, val, act}, so a random minibatch gather costs one/two sectors
+// instead of six.  ret = adv + val is recomputed by the consumer (bit-identical fp32 add).
+// ---------------------------------------------------------------------------------------------
+template <int OP, int RW>
+__global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ done,
+                                                   const float* __restrict__ val, const float* __restrict__ obs,
+                                                   const uint8_t* __restrict__ act, const float* __restrict__ logp,
+                                                   int T, int N, float gamma, float lam, float* __restrict__ adv,
+                                                   float* __restrict__ ret, float* __restrict__ rec) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float last = 0.0f;
+    float v1 = val[(size_t)T * N + n];
+    adv[(size_t)T * N + n] = 0.0f;
+    ret[(size_t)T * N + n] = 0.0f + v1;
+#pragma unroll 4
+    for (int t = T - 1; t >= 0; --t) {
+        const size_t i0 = (size_t)t * N + n, i1 = i0 + N;
+        const float d = (float)done[i1];
+        const float r = rew[i1];
+        const float v0 = val[i0];
+        const float nd = 1.0f - d;
+        const float a = gamma * nd;
+        const float ll = lam * last;
+        const float b = v1 + ll;
+        const float c = a * b;
+        const float dd = r + c;
+        const float ad = dd - v0;
+        adv[i0] = ad;
+        ret[i0] = ad + v0;
+        if (rec != nullptr) {
+            float4* r4 = reinterpret_cast<float4*>(rec + i0 * RW);
+            const float4* o4 = reinterpret_cast<const float4*>(obs + i0 * OP);
+            r4[0] = o4[0];
+            if (RW == 16) {
+                r4[1] = o4[1];
+                r4[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            r4[RW / 4 - 1] = make_float4(logp[i0], ad, v0, __int_as_float((int)act[i0]));
+        }
+        last = ad;
+        v1 = v0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Permutation: idx[i] = cycle-walked alternating Feistel network keyed by Philox.
+// Integer-only => bit-exact with the CPU oracle's restatement.
+// ---------------------------------------------------------------------------------------------
+constexpr int PERM_ROUNDS = 6;
+
+__device__ __forceinline__ uint32_t perm_index(uint32_t i, uint32_t B, uint32_t a, uint32_t b, uint64_t seed,
+                                               uint32_t epoch_ctr, uint32_t rank) {
+    uint32_t x = i;
+    do {
+        uint32_t lb = a, rb = b;
+        uint32_t L = x >> rb, R = x & ((1u << rb) - 1u);
+#pragma unroll
+        for (uint32_t r = 0; r < PERM_ROUNDS; ++r) {
+            const uint4 o = philox_seeded(seed, R, epoch_ctr, r | (rank << 8), TAG_PERM);
+            const uint32_t nR = L ^ (o.x & ((1u << lb) - 1u));
+            L = R;
+            R = nR;
+            const uint32_t t = lb; lb = rb; rb = t;
+        }
+        x = (L << rb) | R;
+    } while (x >= B);
+    return x;
+}
+
+__global__ void __launch_bounds__(256) permutation_kernel(uint32_t* __restrict__ idx, uint32_t B, uint32_t a, uint32_t b,
+                                                           uint64_t seed, uint32_t epoch_ctr, uint32_t rank) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride)
+        idx[i] = perm_index(i, B, a, b, seed, epoch_ctr, rank);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Advantage statistics of every minibatch of one epoch in one launch.  grid = (STAT_PARTS, nmb);
+// each CTA sums its slice in fp64, the last CTA to finish folds the partials in a fixed order
+// (deterministic) and writes mean and unbiased std as fp32.
+// ---------------------------------------------------------------------------------------------
+template <int RW>
+__global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ rec, const uint32_t* __restrict__ idx,
+                                                         uint32_t B, uint32_t mb_size, float* __restrict__ stats_out,
+                                                         double* __restrict__ partials, uint32_t* __restrict__ counter) {
+    const uint32_t mb = blockIdx.y, part = blockIdx.x, nmb = gridDim.y;
+    const uint32_t lo = mb * mb_size;
+    const uint32_t hi = min(B, lo + mb_size);
+    double s = 0.0, ss = 0.0;
+    for (uint32_t i = lo + part * blockDim.x + threadIdx.x; i < hi; i += STAT_PARTS * blockDim.x) {
+        const uint32_t sidx = idx ? idx[i] : i;
+        const double a = (double)rec[(size_t)sidx * RW + (RW - 3)];
+        s += a;
+        ss = fma(a, a, ss);
+    }
+    __shared__ double sh[2][8];
+    __shared__ bool is_last;
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh[0][warp] = s; sh[1][warp] = ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tss = 0.0;
+        for (int w = 0; w < 8; ++w) { ts += sh[0][w]; tss += sh[1][w]; }
+        partials[((size_t)mb * STAT_PARTS + part) * 2 + 0] = ts;
+        partials[((size_t)mb * STAT_PARTS + part) * 2 + 1] = tss;
+        __threadfence();
+        const uint32_t done = atomicAdd(counter, 1u);
+        is_last = (done == nmb * STAT_PARTS - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < nmb) {
+        __threadfence();
+        const uint32_t k = threadIdx.x;
+        double ts = 0.0, tss = 0.0;
+        for (int p = 0; p < STAT_PARTS; ++p) {
+            ts += __ldcg(&partials[((size_t)k * STAT_PARTS + p) * 2 + 0]);
+            tss += __ldcg(&partials[((size_t)k * STAT_PARTS + p) * 2 + 1]);
+        }
+        const uint32_t klo = k * mb_size, khi = min(B, klo + mb_size);
+        const double cnt = (double)(khi - klo);
+        const double mean = ts / cnt;
+        const double var = (tss - ts * mean) / (cnt - 1.0);   // unbiased, torch.std default
+        stats_out[2 * k + 0] = (float)mean;
+        stats_out[2 * k + 1] = (float)sqrt(var > 0.0 ? var : 0.0);
+        if (k == 0) *counter = 0;   // re-arm for the next launch (stream-ordered)
+    }
+}
+
+}  // namespace drl
+
+using namespace drl;
+
+extern "C" {
+
+int drl_gae(const drl_rollout_buf_t* buf, const drl_net_t* net, int32_t T, int32_t N, float gamma, float gae_lambda,
+            float* adv_out, float* ret_out, float* rec_out, void* stream) {
+    int rc = check_net(net);
+    if (rc != DRL_OK) return rc;
+    DRL_REQUIRE(buf && buf->rew && buf->done && buf->val && adv_out && ret_out, "drl_gae: NULL pointer");
+    DRL_REQUIRE(T > 0 && N > 0, "drl_gae: T=%d N=%d", T, N);
+    DRL_REQUIRE(rec_out == nullptr || (buf->obs && buf->act && buf->logp), "drl_gae: record packing needs obs/act/logp");
+    const int blocks = (N + 127) / 128;
+    cudaStream_t st = as_stream(stream);
+    if (net->obs_stride == 4)
+        gae_kernel<4, 8><<<blocks, 128, 0, st>>>(buf->rew, buf->done, buf->val, buf->obs, buf->act, buf->logp, T, N, gamma,
+                                                gae_lambda, adv_out, ret_out, rec_out);
+    else
+        gae_kernel<8, 16><<<blocks, 128, 0, st>>>(buf->rew, buf->done, buf->val, buf->obs, buf->act, buf->logp, T, N, gamma,
+                                                 gae_lambda, adv_out, ret_out, rec_out);
+    DRL_LAUNCH_CHECK("gae_kernel");
+    return DRL_OK;
+}
+
+int drl_permutation(uint32_t* idx_out, uint32_t B, uint64_t seed, uint32_t epoch_ctr, uint32_t rank, void* stream) {
+    DRL_REQUIRE(idx_out, "drl_permutation: idx_out is NULL");
+    DRL_REQUIRE(B > 0 && B <= 0x80000000u, "drl_permutation: B=%u out of range", B);
+    DRL_REQUIRE(rank < (1u << 24), "drl_permutation: rank=%u out of range", rank);
+    uint32_t k = 2;
+    while (k < 32 && (1ull << k) < (unsigned long long)B) ++k;
+    const uint32_t a = k / 2, b = k - a;
+    long long blocks = ((long long)B + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    permutation_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(idx_out, B, a, b, seed, epoch_ctr, rank);
+    DRL_LAUNCH_CHECK("permutation_kernel");
+    return DRL_OK;
+}
+
+int drl_adv_stats(const drl_net_t* net, const float* rec, const uint32_t* idx, uint32_t B, uint32_t mb_size,
+                  float* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_net(net);
+    if (rc != DRL_OK) return rc;
+    DRL_REQUIRE(rec && stats_out && workspace, "drl_adv_stats: NULL pointer");
+    DRL_REQUIRE(B > 0 && mb_size > 0, "drl_adv_stats: B=%u mb_size=%u", B, mb_size);
+    const uint32_t nmb = (B + mb_size - 1) / mb_size;
+    DRL_REQUIRE(nmb <= (uint32_t)MAX_MINIBATCHES, "drl_adv_stats: %u minibatches > %d", nmb, MAX_MINIBATCHES);
+    const WorkspaceLayout w = workspace_layout(drl_param_count(net));
+    DRL_REQUIRE(workspace_bytes >= w.total, "drl_adv_stats: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    uint32_t* counter = reinterpret_cast<uint32_t*>((char*)workspace + w.counters);
+    double* partials = reinterpret_cast<double*>((char*)workspace + w.stat_partials);
+    dim3 grid(STAT_PARTS, nmb);
+    if (net->obs_dim <= 4) adv_stats_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(rec, idx, B, mb_size, stats_out, partials, counter);
+    else adv_stats_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(rec, idx, B, mb_size, stats_out, partials, counter);
+    DRL_LAUNCH_CHECK("adv_stats_kernel");
+    return DRL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// rollout.cu -- the fused rollout kernel: T x (actor + critic forward, Philox categorical sample,
+// log-prob, env step with auto-reset + episode statistics, SoA stores), deep_rl/ppo.py:110-141.
+//
+// One launch covers the whole rollout: a warp owns 8*SUB environments for all T steps, so there is no
+// grid-wide synchronisation; env state lives in registers (float64, like gym), weights in shared
+// memory (36.9 KB, staged once by TMA bulk copy).  Per env-step the kernel writes obs 16/32 B +
+// act 1 B + logp 4 B + val 4 B + rew 4 B + done 1 B to the [T+1][N] planes and reads nothing from HBM.
+#include "drl_env.cuh"
+#include "drl_mlp.cuh"
+#include "drl_pack.cuh"
+
+namespace drl {
+
+int check_env(const drl_env_t* env);
+drl_ep_log_t log_or_empty(const drl_ep_log_t* log);
+
+constexpr int RO_WARPS = 4;
+
+template <int KIND, int SUB>
+__global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(drl_env_t env, const float* __restrict__ packed, int T,
+                                                                uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log) {
+    using S = EnvSpec<KIND>;
+    constexpr int O = S::O, A = S::A, OP = S::OP;
+    using P = Packed<O, A>;
+    constexpr int EPW = TILE * SUB;                       // envs per warp
+    constexpr int WS = SUB * OBS_S + H1_S + SUB * OUT_S;  // per-warp scratch floats
+
+    extern __shared__ __align__(128) float smem[];
+    float* sw = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P::FWD);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* obs_s = smem + P::FWD + 4 + warp * WS;
+    float* h1_s = obs_s + SUB * OBS_S;
+    float* out_s = h1_s + H1_S;
+    stage_params(sw, packed, P::FWD, bar);
+
+    const int N = env.num_envs;
+    const int env0 = (blockIdx.x * RO_WARPS + warp) * EPW;
+    if (env0 >= N) return;
+    const int n = env0 + lane;
+    const bool own = lane < EPW && n < N;
+    const uint32_t gid = env.env_gid0 + (uint32_t)n;
+
+    EnvLane e;
+    e.s[0] = e.s[1] = e.s[2] = e.s[3] = 0.0; e.elapsed = 0; e.ep_ret = 0.0f; e.ep_len = 0;
+    if (own) env_load(e, env, n);
+
+    for (int t = 0; t <= T; ++t) {
+        // ---- observation of the current state: to HBM (obs[t]) and to the warp's input tile ----
+        if (lane < EPW) {
+            float obs[OP];
+#pragma unroll
+            for (int i = 0; i < OP; ++i) obs[i] = 0.0f;
+            if (own) {
+                env_observation<KIND>(e.s, obs);
+                float4* o4 = reinterpret_cast<float4*>(buf.obs + ((size_t)t * N + n) * OP);
+#pragma unroll
+                for (int q = 0; q < OP / 4; ++q) o4[q] = make_float4(obs[4 * q], obs[4 * q + 1], obs[4 * q + 2], obs[4 * q + 3]);
+            }
+            float* dst = obs_s + (lane >> 3) * OBS_S + (lane & 7);
+#pragma unroll
+            for (int i = 0; i < O; ++i) dst[i * TILE] = obs[i];
+        }
+        __syncwarp();
+
+        // ---- actor + critic forward for the warp's SUB tiles ----
+#pragma unroll
+        for (int sub = 0; sub < SUB; ++sub) {
+            float h2[TILE][UPL];
+            mlp_forward_tile<O, A>(sw, obs_s + sub * OBS_S, h1_s, out_s + sub * OUT_S, lane, h2);
+        }
+
+        // ---- per-env tail: value store, sample, env step ----
+        if (own) {
+            const size_t i0 = (size_t)t * N + n;
+            buf.val[i0] = out_s[lane * OUT_W + 3];
+            if (t < T) {
+                float l[A];
+#pragma unroll
+                for (int a = 0; a < A; ++a) l[a] = out_s[lane * OUT_W + a];
+                const uint64_t step = step0 + (uint64_t)t;
+                const uint4 r = philox_seeded(env.seed, gid, (uint32_t)step, (uint32_t)(step >> 32), TAG_ACTION);
+                float lp;
+                const int act = sample_categorical<A>(l, u01_f32(r.x), lp);
+                buf.act[i0] = (uint8_t)act;
+                buf.logp[i0] = lp;
+                float reward;
+                const bool done = env_step<KIND>(e, act, reward, env.seed, gid, step, env.max_episode_steps, log);
+                buf.rew[i0 + N] = reward;
+                buf.done[i0 + N] = done ? 1 : 0;
+            }
+        }
+        __syncwarp();
+    }
+    if (own) env_store(e, env, n);
+}
+
+template <int KIND, int SUB>
+int launch_rollout(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
+                   const drl_ep_log_t& log, cudaStream_t st) {
+    using S = EnvSpec<KIND>;
+    constexpr int WS = SUB * OBS_S + H1_S + SUB * OUT_S;
+    const size_t smem = sizeof(float) * (Packed<S::O, S::A>::FWD + 4 + RO_WARPS * WS);
+    DRL_CUDA(cudaFuncSetAttribute(rollout_kernel<KIND, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int epc = TILE * SUB * RO_WARPS;
+    const int blocks = (env.num_envs + epc - 1) / epc;
+    rollout_kernel<KIND, SUB><<<blocks, RO_WARPS * 32, smem, st>>>(env, packed, T, step0, buf, log);
+    DRL_LAUNCH_CHECK("rollout_kernel");
+    return DRL_OK;
+}
+
+// envs per warp: small N wants as many warps as possible (latency-bound), large N amortises the
+// 8-lane env/sampling tail over more tiles.
+int pick_sub(int N) {
+    const char* ov = getenv("DRL_ROLLOUT_SUB");
+    if (ov) { int v = atoi(ov); if (v == 1 || v == 2 || v == 4) return v; }
+    const int warps_at_1 = (N + TILE - 1) / TILE;
+    const int sms = sm_count();
+    if (warps_at_1 <= sms * 24) return 1;
+    if (warps_at_1 <= sms * 48) return 2;
+    return 4;
+}
+
+}  // namespace drl
+
+using namespace drl;
+
+extern "C" int drl_rollout(const drl_env_t* env, const drl_net_t* net, const float* packed, int32_t T, uint64_t step0,
+                           const drl_rollout_buf_t* buf, const drl_ep_log_t* log, void* stream) {
+    int rc = check_env(env);
+    if (rc != DRL_OK) return rc;
+    rc = check_net(net);
+    if (rc != DRL_OK) return rc;
+    DRL_REQUIRE(packed && buf, "drl_rollout: NULL pointer");
+    DRL_REQUIRE(buf->obs && buf->act && buf->logp && buf->val && buf->rew && buf->done, "drl_rollout: NULL buffer plane");
+    DRL_REQUIRE(T > 0, "drl_rollout: T=%d", T);
+    DRL_REQUIRE(net->obs_dim == drl_env_obs_dim(env->kind) && net->num_actions == drl_env_num_actions(env->kind),
+                "drl_rollout: net shape does not match env kind %d", env->kind);
+    const drl_ep_log_t l = log_or_empty(log);
+    const int sub = pick_sub(env->num_envs);
+    cudaStream_t st = as_stream(stream);
+    if (env->kind == DRL_ENV_CARTPOLE) {
+        if (sub == 1) return launch_rollout<DRL_ENV_CARTPOLE, 1>(*env, packed, T, step0, *buf, l, st);
+        if (sub == 2) return launch_rollout<DRL_ENV_CARTPOLE, 2>(*env, packed, T, step0, *buf, l, st);
+        return launch_rollout<DRL_ENV_CARTPOLE, 4>(*env, packed, T, step0, *buf, l, st);
+    }
+    if (sub == 1) return launch_rollout<DRL_ENV_ACROBOT, 1>(*env, packed, T, step0, *buf, l, st);
+    if (sub == 2) return launch_rollout<DRL_ENV_ACROBOT, 2>(*env, packed, T, step0, *buf, l, st);
+    return launch_rollout<DRL_ENV_ACROBOT, 4>(*env, packed, T, step0, *buf, l, st);
+}

@@ -1,0 +1,493 @@
+// update_ops.cu -- one PPO minibatch step on the GPU (deep_rl/ppo.py:159-192):
+//   ppo_grad_kernel   gather records by index -> actor+critic forward -> clipped-surrogate / value /
+//                     entropy loss (ppo.py:166-187) -> closed-form backward ->
+//                     per-CTA partial gradients (FP32 CUDA-core path)
+//   grad_reduce_kernel fixed-order sum of the per-CTA partials -> flat gradient + loss terms
+//   clip_adam_kernel  clip_grad_norm_ + Adam (+ refresh of the packed kernel layout), ppo.py:191-192
+#include "drl_mlp.cuh"
+#include "drl_pack.cuh"
+
+namespace drl {
+
+constexpr int GW = 8;                 // warps per CTA
+constexpr int GT = GW * 32;           // threads per CTA
+constexpr int CTA_TILE = GW * TILE;   // samples per CTA tile
+constexpr int DZ2_S = H1_S;           // floats: dz2 tile [net][o][e]
+constexpr int DOUT_S = 64;            // floats: dout tile [net][e][4]
+constexpr int WS_G = OBS_S + H1_S + DZ2_S + OUT_S + DOUT_S;
+
+template <int O, int A>
+struct GradLocal {                    // lane-local gradient accumulators (units u + 16 j of one net)
+    static constexpr int N = 4 * O + 8 + 5 * A;
+    float w1[UPL][O];
+    float b1[UPL];
+    float b2[UPL];
+    float w4[A][UPL];
+    float b4[A];
+};
+
+struct GradArgs {
+    const float* packed;
+    const float* rec;
+    const uint32_t* idx;
+    uint32_t mb_start, mb_count;
+    const float* adv_stats;   // [2] mean, std
+    float clip_coef, ent_coef, vf_coef;
+    float* grad_part;         // [gridDim.x][ppad]
+    float* loss_part;         // [gridDim.x][LOSS_TERMS]
+    int ppad;
+};
+
+template <int O, int A, int OP, int RW>
+__global__ void __launch_bounds__(GT, 1) ppo_grad_kernel(GradArgs g) {
+    using P = Packed<O, A>;
+    extern __shared__ __align__(128) float smem[];
+    float* sw = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + P::ALL);
+    float* scratch = smem + P::ALL + 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* obs_s = scratch + warp * WS_G;
+    float* h1_s = obs_s + OBS_S;
+    float* dz2_s = h1_s + H1_S;
+    float* out_s = dz2_s + DZ2_S;
+    float* dout_s = out_s + OUT_S;
+    stage_params(sw, g.packed, P::ALL, bar);
+
+    const int net = lane >> 4, u = lane & 15;
+    const float adv_mean = g.adv_stats[0], adv_std = g.adv_stats[1];
+    const float inv_m = 1.0f / (float)g.mb_count;
+
+    // phase-B ownership: dW2[net_b][o][i] patch of 4 (o) x 8 (i)
+    const int net_b = warp >> 2, ob = (warp >> 1) & 1, ib = warp & 1, og = lane & 7, ig = lane >> 3;
+    float acc2[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc2[a][b] = 0.0f;
+
+    GradLocal<O, A> gl;
+#pragma unroll
+    for (int j = 0; j < UPL; ++j) {
+#pragma unroll
+        for (int i = 0; i < O; ++i) gl.w1[j][i] = 0.0f;
+        gl.b1[j] = 0.0f; gl.b2[j] = 0.0f;
+#pragma unroll
+        for (int a = 0; a < A; ++a) gl.w4[a][j] = 0.0f;
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) gl.b4[a] = 0.0f;
+    float s_pg = 0.f, s_v = 0.f, s_ent = 0.f, s_kl = 0.f, s_clip = 0.f;
+
+    const uint32_t ntiles = (g.mb_count + CTA_TILE - 1) / CTA_TILE;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- A0: gather the warp's 8 sample records ----
+        float logp_old = 0.f, adv = 0.f, val_old = 0.f;
+        int act = 0;
+        bool valid = false;
+        if (lane < TILE) {
+            const uint32_t pos = tile * CTA_TILE + warp * TILE + lane;
+            valid = pos < g.mb_count;
+            float x[OP];
+#pragma unroll
+            for (int i = 0; i < OP; ++i) x[i] = 0.0f;
+            if (valid) {
+                const uint32_t i = g.mb_start + pos;
+                const size_t s = g.idx ? g.idx[i] : i;
+                const float4* r4 = reinterpret_cast<const float4*>(g.rec + s * RW);
+#pragma unroll
+                for (int q = 0; q < OP / 4; ++q) {
+                    const float4 v = __ldg(r4 + q);
+                    x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+                }
+                const float4 t4 = __ldg(r4 + RW / 4 - 1);
+                logp_old = t4.x; adv = t4.y; val_old = t4.z; act = __float_as_int(t4.w);
+            }
+#pragma unroll
+            for (int i = 0; i < O; ++i) obs_s[i * TILE + lane] = x[i];
+        }
+        __syncwarp();
+
+        // ---- A1: forward ----
+        float h2[TILE][UPL];
+        mlp_forward_tile<O, A>(sw, obs_s, h1_s, out_s, lane, h2);
+
+        // ---- A2: loss and output gradients, one sample per lane (lanes 0-7) ----
+        if (lane < TILE) {
+            float dl[4] = {0.f, 0.f, 0.f, 0.f};
+            float dv = 0.f;
+            if (valid) {
+                float l[A];
+#pragma unroll
+                for (int a = 0; a < A; ++a) l[a] = out_s[lane * OUT_W + a];
+                const float v = out_s[lane * OUT_W + 3];
+                float m = l[0];
+#pragma unroll
+                for (int a = 1; a < A; ++a) m = fmaxf(m, l[a]);
+                float se = 0.f;
+#pragma unroll
+                for (int a = 0; a < A; ++a) se += expf(l[a] - m);
+                const float lse = m + logf(se);
+                float lp[A], p[A];
+                float ent = 0.f, new_logp = 0.f;
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    lp[a] = l[a] - lse;
+                    p[a] = expf(lp[a]);
+                    ent -= p[a] * lp[a];
+                    if (a == act) new_logp = lp[a];
+                }
+                const float nadv = (adv - adv_mean) / (adv_std + 1e-8f);
+                const float logratio = new_logp - logp_old;
+                const float ratio = expf(logratio);
+                const float pg1 = -nadv * ratio;
+                const float pg2 = -nadv * fminf(fmaxf(ratio, 1.0f - g.clip_coef), 1.0f + g.clip_coef);
+                const float dpg = pg1 >= pg2 ? pg1 : 0.0f;   // d max(pg1,pg2) / d new_logp  (= -nadv*ratio)
+                const float ret = adv + val_old;             // returns = advantages + values, ppo.py:151
+                const float vd = v - ret;
+                const float vu = vd * vd;
+                const float vc = val_old + fminf(fmaxf(v - val_old, -g.clip_coef), g.clip_coef);
+                const float vcd = vc - ret;
+                const float vcl = vcd * vcd;
+                s_pg += fmaxf(pg1, pg2);
+                s_v += fmaxf(vu, vcl);
+                s_ent += ent;
+                s_kl += (ratio - 1.0f) - logratio;
+                s_clip += fabsf(ratio - 1.0f) > g.clip_coef ? 1.0f : 0.0f;
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    const float onehot = a == act ? 1.0f : 0.0f;
+                    dl[a] = inv_m * (dpg * (onehot - p[a]) + g.ent_coef * p[a] * (lp[a] + ent));
+                }
+                dv = vu >= vcl ? g.vf_coef * vd * inv_m : 0.0f;
+            }
+            *reinterpret_cast<float4*>(dout_s + lane * 4) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+            *reinterpret_cast<float4*>(dout_s + (TILE + lane) * 4) = make_float4(dv, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+
+        // ---- A3: head backward; dz2 = (dout . W4) * (1 - h2^2) ----
+        {
+            float d[TILE][A];
+#pragma unroll
+            for (int e = 0; e < TILE; ++e) {
+                const float4 t4 = *reinterpret_cast<const float4*>(dout_s + (net * TILE + e) * 4);
+                const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                for (int a = 0; a < A; ++a) d[e][a] = tt[a];
+            }
+            float dz2[TILE][UPL];
+#pragma unroll
+            for (int e = 0; e < TILE; ++e)
+#pragma unroll
+                for (int j = 0; j < UPL; ++j) dz2[e][j] = 0.0f;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const float4 w = *reinterpret_cast<const float4*>(sw + P::W4 + (net * A + a) * H + 4 * u);
+                const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int e = 0; e < TILE; ++e) {
+                    gl.b4[a] += d[e][a];
+#pragma unroll
+                    for (int j = 0; j < UPL; ++j) {
+                        gl.w4[a][j] = fmaf(d[e][a], h2[e][j], gl.w4[a][j]);
+                        dz2[e][j] = fmaf(d[e][a], ww[j], dz2[e][j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UPL; ++j) {
+#pragma unroll
+                for (int e = 0; e < TILE; ++e) {
+                    dz2[e][j] *= fmaf(-h2[e][j], h2[e][j], 1.0f);
+                    gl.b2[j] += dz2[e][j];
+                }
+                float* row = dz2_s + (net * H + u + 16 * j) * TILE;
+                *reinterpret_cast<float4*>(row) = make_float4(dz2[0][j], dz2[1][j], dz2[2][j], dz2[3][j]);
+                *reinterpret_cast<float4*>(row + 4) = make_float4(dz2[4][j], dz2[5][j], dz2[6][j], dz2[7][j]);
+            }
+        }
+        __syncwarp();
+
+        // ---- A4: dh1 = dz2 . W2 ; dz1 = dh1 * (1 - h1^2) ; layer-1 weight gradients ----
+        {
+            float acc[TILE][UPL];
+#pragma unroll
+            for (int e = 0; e < TILE; ++e)
+#pragma unroll
+                for (int j = 0; j < UPL; ++j) acc[e][j] = 0.0f;
+            const float* wp = sw + P::W2P + net * H * H + 4 * u;
+            const float* ap = dz2_s + net * H * TILE;
+#pragma unroll 8
+            for (int o = 0; o < H; ++o) {
+                const float4 w = *reinterpret_cast<const float4*>(wp + o * H);
+                const float4 x0 = *reinterpret_cast<const float4*>(ap + o * TILE);
+                const float4 x1 = *reinterpret_cast<const float4*>(ap + o * TILE + 4);
+                const float xs[TILE] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int e = 0; e < TILE; ++e) {
+                    acc[e][0] = fmaf(xs[e], w.x, acc[e][0]);
+                    acc[e][1] = fmaf(xs[e], w.y, acc[e][1]);
+                    acc[e][2] = fmaf(xs[e], w.z, acc[e][2]);
+                    acc[e][3] = fmaf(xs[e], w.w, acc[e][3]);
+                }
+            }
+            float xo[O][TILE];
+#pragma unroll
+            for (int i = 0; i < O; ++i) {
+                const float4 x0 = *reinterpret_cast<const float4*>(obs_s + i * TILE);
+                const float4 x1 = *reinterpret_cast<const float4*>(obs_s + i * TILE + 4);
+                xo[i][0] = x0.x; xo[i][1] = x0.y; xo[i][2] = x0.z; xo[i][3] = x0.w;
+                xo[i][4] = x1.x; xo[i][5] = x1.y; xo[i][6] = x1.z; xo[i][7] = x1.w;
+            }
+#pragma unroll
+            for (int j = 0; j < UPL; ++j) {
+                const float* row = h1_s + (net * H + u + 16 * j) * TILE;
+                const float4 a0 = *reinterpret_cast<const float4*>(row);
+                const float4 a1 = *reinterpret_cast<const float4*>(row + 4);
+                const float hv[TILE] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int e = 0; e < TILE; ++e) {
+                    const float dz1 = acc[e][j] * fmaf(-hv[e], hv[e], 1.0f);
+                    gl.b1[j] += dz1;
+#pragma unroll
+                    for (int i = 0; i < O; ++i) gl.w1[j][i] = fmaf(dz1, xo[i][e], gl.w1[j][i]);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- B: dW2[o][i] += sum over the CTA's 64 samples of dz2[s][o] * h1[s][i] ----
+#pragma unroll 1
+        for (int w = 0; w < GW; ++w) {
+            const float* hs = scratch + w * WS_G + OBS_S + net_b * H * TILE;
+            const float* ds = hs + H1_S;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float4 dz[4], hh[8];
+#pragma unroll
+                for (int jo = 0; jo < 4; ++jo)
+                    dz[jo] = *reinterpret_cast<const float4*>(ds + (ob * 32 + og + 8 * jo) * TILE + 4 * q);
+#pragma unroll
+                for (int ii = 0; ii < 8; ++ii)
+                    hh[ii] = *reinterpret_cast<const float4*>(hs + (ib * 32 + ig + 4 * ii) * TILE + 4 * q);
+#pragma unroll
+                for (int jo = 0; jo < 4; ++jo)
+#pragma unroll
+                    for (int ii = 0; ii < 8; ++ii)
+                        acc2[jo][ii] = fmaf(dz[jo].w, hh[ii].w, fmaf(dz[jo].z, hh[ii].z,
+                                       fmaf(dz[jo].y, hh[ii].y, fmaf(dz[jo].x, hh[ii].x, acc2[jo][ii]))));
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: per-CTA partial gradient in canonical layout ----
+    float* part = g.grad_part + (size_t)blockIdx.x * g.ppad;
+    {
+        const int nb = net_b * P::C_ACTOR + H * O + H;   // canonical offset of W2 of net_b
+#pragma unroll
+        for (int jo = 0; jo < 4; ++jo)
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii)
+                part[nb + (ob * 32 + og + 8 * jo) * H + (ib * 32 + ig + 4 * ii)] = acc2[jo][ii];
+    }
+    // lane-local accumulators: fold the 8 warps through shared memory (scratch is free now)
+    constexpr int NL = GradLocal<O, A>::N;
+    float* red = scratch;   // [GW][32][NL]
+    {
+        float* mine = red + (warp * 32 + lane) * NL;
+        int k = 0;
+#pragma unroll
+        for (int j = 0; j < UPL; ++j)
+#pragma unroll
+            for (int i = 0; i < O; ++i) mine[k++] = gl.w1[j][i];
+#pragma unroll
+        for (int j = 0; j < UPL; ++j) mine[k++] = gl.b1[j];
+#pragma unroll
+        for (int j = 0; j < UPL; ++j) mine[k++] = gl.b2[j];
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+            for (int j = 0; j < UPL; ++j) mine[k++] = gl.w4[a][j];
+#pragma unroll
+        for (int a = 0; a < A; ++a) mine[k++] = gl.b4[a];
+    }
+    __syncthreads();
+    for (int item = tid; item < 32 * NL; item += GT) {
+        const int ln = item / NL, k = item % NL;
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < GW; ++w) s += red[(w * 32 + ln) * NL + k];
+        const int nt = ln >> 4, uu = ln & 15;
+        const int base = nt * P::C_ACTOR;
+        const int nout = nt == 0 ? A : 1;
+        int canon = -1;
+        if (k < UPL * O) {
+            const int j = k / O, i = k % O;
+            canon = base + (uu + 16 * j) * O + i;
+        } else if (k < UPL * O + UPL) {
+            canon = base + H * O + (uu + 16 * (k - UPL * O));
+        } else if (k < UPL * O + 2 * UPL) {
+            canon = base + H * O + H + H * H + (uu + 16 * (k - UPL * O - UPL));
+        } else if (k < UPL * O + 2 * UPL + A * UPL) {
+            const int kk = k - (UPL * O + 2 * UPL);
+            const int a = kk / UPL, j = kk % UPL;
+            if (a < nout) canon = base + P::C_NET + a * H + (uu + 16 * j);
+        } else {
+            const int a = k - (UPL * O + 2 * UPL + A * UPL);
+            if (uu == 0 && a < nout) canon = base + P::C_NET + nout * H + a;
+        }
+        if (canon >= 0) part[canon] = s;
+    }
+    // loss-term partial sums
+    __shared__ float lsum[GW][5];
+    {
+        const float t0 = warp_sum(s_pg), t1 = warp_sum(s_v), t2 = warp_sum(s_ent), t3 = warp_sum(s_kl), t4 = warp_sum(s_clip);
+        if (lane == 0) { lsum[warp][0] = t0; lsum[warp][1] = t1; lsum[warp][2] = t2; lsum[warp][3] = t3; lsum[warp][4] = t4; }
+    }
+    __syncthreads();
+    if (tid < 5) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < GW; ++w) s += lsum[w][tid];
+        g.loss_part[blockIdx.x * LOSS_TERMS + tid] = s;
+    }
+}
+
+// Sum the per-CTA partials in a fixed order (deterministic) and finish the loss terms.
+__global__ void __launch_bounds__(256) grad_reduce_kernel(const float* __restrict__ grad_part, const float* __restrict__ loss_part,
+                                                           int nparts, int ppad, int P, uint32_t mb_count, float ent_coef,
+                                                           float vf_coef, float* __restrict__ grad_out,
+                                                           float* __restrict__ loss_terms_out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) {
+        float s = 0.0f;
+        for (int c = 0; c < nparts; ++c) s += grad_part[(size_t)c * ppad + p];
+        grad_out[p] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss_terms_out != nullptr) {
+        float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < nparts; ++c)
+            for (int k = 0; k < 5; ++k) t[k] += loss_part[c * LOSS_TERMS + k];
+        const float inv = 1.0f / (float)mb_count;
+        const float pg = t[0] * inv, vl = 0.5f * t[1] * inv, en = t[2] * inv;
+        loss_terms_out[0] = pg - ent_coef * en + vl * vf_coef;
+        loss_terms_out[1] = pg;
+        loss_terms_out[2] = vl;
+        loss_terms_out[3] = en;
+        loss_terms_out[4] = t[3] * inv;
+        loss_terms_out[5] = t[4] * inv;
+        loss_terms_out[6] = 0.0f;
+        loss_terms_out[7] = 0.0f;
+    }
+}
+
+// clip_grad_norm_ + Adam.  Every CTA recomputes the global norm from the (L2-resident) gradient in
+// the same order, so no grid-wide synchronisation is needed and all CTAs agree bit-for-bit.
+struct AdamArgs {
+    float* params; const float* grad; float* m; float* v; float* packed; float* norm_out;
+    int P;
+    float grad_scale, max_norm, beta2, om_beta1, om_beta2, eps, neg_step_size, bc2_sqrt;
+};
+
+template <int O, int A>
+__global__ void __launch_bounds__(256) clip_adam_kernel(AdamArgs a) {
+    __shared__ double sh[8];
+    __shared__ float s_coef;
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < a.P; i += blockDim.x) {
+        const double gv = (double)(a.grad[i] * a.grad_scale);
+        ss = fma(gv, gv, ss);
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        const float norm = (float)sqrt(t);
+        const float c = a.max_norm / (norm + 1e-6f);
+        s_coef = c < 1.0f ? c : 1.0f;
+        if (blockIdx.x == 0 && a.norm_out) *a.norm_out = norm;
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.P) return;
+    const float gsc = (a.grad[i] * a.grad_scale) * coef;
+    float m = a.m[i], v = a.v[i], p = a.params[i];
+    m = m + a.om_beta1 * (gsc - m);                        // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * a.beta2 + (a.om_beta2 * gsc) * gsc;            // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    p = p + (a.neg_step_size * m) / denom;                 // param.addcdiv_(exp_avg, denom, value=-step_size)
+    a.m[i] = m; a.v[i] = v; a.params[i] = p;
+    if (a.packed != nullptr) packed_store<O, A>(a.packed, i, p);
+}
+
+template <int O, int A, int OP, int RW>
+int launch_grad(const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (Packed<O, A>::ALL + 4 + GW * WS_G);
+    DRL_CUDA(cudaFuncSetAttribute(ppo_grad_kernel<O, A, OP, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t ntiles = (g.mb_count + CTA_TILE - 1) / CTA_TILE;
+    int grid = sm_count();
+    if (grid > MAX_GRAD_CTAS) grid = MAX_GRAD_CTAS;
+    if ((uint32_t)grid > ntiles) grid = (int)ntiles;
+    ppo_grad_kernel<O, A, OP, RW><<<grid, GT, smem, st>>>(g);
+    DRL_LAUNCH_CHECK("ppo_grad_kernel");
+    grad_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(g.grad_part, g.loss_part, grid, g.ppad, P, g.mb_count, g.ent_coef,
+                                                       g.vf_coef, grad_out, loss_terms_out);
+    DRL_LAUNCH_CHECK("grad_reduce_kernel");
+    return DRL_OK;
+}
+
+}  // namespace drl
+
+using namespace drl;
+
+extern "C" {
+
+int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const float* rec, const uint32_t* idx,
+                           uint32_t mb_start, uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef,
+                           float* grad_out, float* loss_terms_out, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_net(net);
+    if (rc != DRL_OK) return rc;
+    DRL_REQUIRE(packed && rec && adv_stats && coef && grad_out && workspace, "drl_ppo_minibatch_grad: NULL pointer");
+    DRL_REQUIRE(mb_count > 0, "drl_ppo_minibatch_grad: empty minibatch");
+    const int P = (int)drl_param_count(net);
+    const WorkspaceLayout w = workspace_layout(P);
+    DRL_REQUIRE(workspace_bytes >= w.total, "drl_ppo_minibatch_grad: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    GradArgs g;
+    g.packed = packed; g.rec = rec; g.idx = idx; g.mb_start = mb_start; g.mb_count = mb_count; g.adv_stats = adv_stats;
+    g.clip_coef = coef->clip_coef; g.ent_coef = coef->ent_coef; g.vf_coef = coef->vf_coef;
+    g.grad_part = reinterpret_cast<float*>((char*)workspace + w.grad_partials);
+    g.loss_part = reinterpret_cast<float*>((char*)workspace + w.loss_partials);
+    g.ppad = w.ppad;
+    if (net->obs_dim == 4) return launch_grad<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, as_stream(stream));
+    return launch_grad<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, as_stream(stream));
+}
+
+int drl_clip_adam(const drl_net_t* net, float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t step,
+                  double lr, double beta1, double beta2, double eps, double max_grad_norm, double grad_scale,
+                  float* packed_out, float* norm_out, void* stream) {
+    int rc = check_net(net);
+    if (rc != DRL_OK) return rc;
+    DRL_REQUIRE(params && grad && exp_avg && exp_avg_sq, "drl_clip_adam: NULL pointer");
+    DRL_REQUIRE(step >= 1, "drl_clip_adam: step=%lld must be >= 1", (long long)step);
+    AdamArgs a;
+    a.params = params; a.grad = grad; a.m = exp_avg; a.v = exp_avg_sq; a.packed = packed_out; a.norm_out = norm_out;
+    a.P = (int)drl_param_count(net);
+    a.grad_scale = (float)grad_scale; a.max_norm = (float)max_grad_norm;
+    a.beta2 = (float)beta2; a.om_beta1 = (float)(1.0 - beta1); a.om_beta2 = (float)(1.0 - beta2); a.eps = (float)eps;
+    // scalars exactly as torch.optim.adam._single_tensor_adam computes them (Python floats, fp64)
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    a.neg_step_size = (float)(-(lr / bc1));
+    a.bc2_sqrt = (float)sqrt(bc2);
+    const int blocks = (a.P + 255) / 256;
+    if (net->obs_dim == 4) clip_adam_kernel<4, 2><<<blocks, 256, 0, as_stream(stream)>>>(a);
+    else clip_adam_kernel<6, 3><<<blocks, 256, 0, as_stream(stream)>>>(a);
+    DRL_LAUNCH_CHECK("clip_adam_kernel");
+    return DRL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+"""Device-resident batched CartPole-v1 / Acrobot-v1 with the gym-0.21 4-tuple API.
+
+Replaces `gym.wrappers.RecordEpisodeStatistics(gym.make(env_id))` + `TorchWrapper`
+(deep_rl/ppo.py:10-22,79-80) and the manual auto-reset of ppo.py:127-129 for `num_envs`
+environments.  With num_envs == 1 a step returns what the reference's wrapper chain returns (obs
+tensor, reward, done, info with info["episode"]["r"|"l"] on episode end), except that the reset
+after `done` has already happened inside the kernel (SyncVectorEnv semantics): the returned
+observation is the first observation of the next episode, so the caller must NOT call reset() again.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+ENV_KINDS = {"CartPole-v1": 0, "Acrobot-v1": 1}
+MAX_EPISODE_STEPS = {"CartPole-v1": 500, "Acrobot-v1": 500}
+
+
+class EpisodeLog:
+    """Finished-episode log written by the kernels (drl_ep_log_t)."""
+
+    def __init__(self, cap: int, device):
+        self.cap = int(cap)
+        self.count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.sums = torch.zeros(2, dtype=torch.float64, device=device)      # sum_ret, sum_len
+        self.ret = torch.zeros(self.cap, dtype=torch.float32, device=device)
+        self.len = torch.zeros(self.cap, dtype=torch.int32, device=device)
+        self.env = torch.zeros(self.cap, dtype=torch.int32, device=device)
+        self.step = torch.zeros(self.cap, dtype=torch.int64, device=device)
+        self.struct = _lib.EpLogT(self.count.data_ptr(), self.sums.data_ptr(), self.sums.data_ptr() + 8,
+                                  self.ret.data_ptr(), self.len.data_ptr(), self.env.data_ptr(), self.step.data_ptr(),
+                                  self.cap)
+
+    def drain(self):
+        """D2H read + clear.  Returns (count, sum_ret, sum_len, entries sorted by (step, env))."""
+        n = int(self.count.item())
+        sums = self.sums.tolist()
+        k = min(n, self.cap)
+        entries = []
+        if k:
+            st, ev = self.step[:k].tolist(), self.env[:k].tolist()
+            rt, ln = self.ret[:k].tolist(), self.len[:k].tolist()
+            entries = sorted(zip(st, ev, rt, ln))
+        self.count.zero_()
+        self.sums.zero_()
+        return n, sums[0], sums[1], entries
+
+
+class VecEnv:
+    """`num_envs` independent environments stepping in one kernel launch."""
+
+    def __init__(self, env_id: str = "CartPole-v1", num_envs: int = 1, seed: int = 1, env_gid0: int = 0,
+                 device: Optional[torch.device] = None, log_capacity: int = 1 << 16):
+        if env_id not in ENV_KINDS:
+            raise ValueError(f"unsupported env_id {env_id!r}; supported: {sorted(ENV_KINDS)}")
+        _lib.require_cuda()
+        self.L = _lib.lib()
+        self.env_id, self.kind = env_id, ENV_KINDS[env_id]
+        self.num_envs, self.env_gid0 = int(num_envs), int(env_gid0)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.obs_dim = self.L.drl_env_obs_dim(self.kind)
+        self.num_actions = self.L.drl_env_num_actions(self.kind)
+        self.obs_stride = self.L.drl_env_obs_stride(self.kind)
+        self.observation_space = SimpleNamespace(shape=(self.obs_dim,), dtype=torch.float32)
+        self.action_space = SimpleNamespace(n=self.num_actions, shape=(), dtype=torch.int64)
+        N = self.num_envs
+        self.state = torch.zeros((4, N), dtype=torch.float64, device=self.device)
+        self.elapsed = torch.zeros(N, dtype=torch.int32, device=self.device)
+        self.ep_ret = torch.zeros(N, dtype=torch.float32, device=self.device)
+        self.ep_len = torch.zeros(N, dtype=torch.int32, device=self.device)
+        self.log = EpisodeLog(log_capacity, self.device)
+        self.step_count = 0          # global step index fed to the Philox counter
+        self._seed = int(seed)
+        self._obs = torch.zeros((N, self.obs_stride), dtype=torch.float32, device=self.device)
+        self._rew = torch.zeros(N, dtype=torch.float32, device=self.device)
+        self._done = torch.zeros(N, dtype=torch.uint8, device=self.device)
+        self._struct = None
+
+    # -- gym surface ------------------------------------------------------------------------
+    def seed(self, seed: int):
+        self._seed = int(seed)
+        self._struct = None
+        return [seed]
+
+    @property
+    def struct(self) -> _lib.EnvT:
+        if self._struct is None:
+            self._struct = _lib.EnvT(self.kind, self.num_envs, self._seed, self.env_gid0, MAX_EPISODE_STEPS[self.env_id],
+                                     self.state.data_ptr(), self.elapsed.data_ptr(), self.ep_ret.data_ptr(),
+                                     self.ep_len.data_ptr())
+        return self._struct
+
+    def _view(self, obs: torch.Tensor) -> torch.Tensor:
+        o = obs[:, : self.obs_dim]
+        return o[0] if self.num_envs == 1 else o
+
+    def reset(self) -> torch.Tensor:
+        _lib.check(self.L.drl_env_reset(C.byref(self.struct), self._obs.data_ptr(), _lib.stream_ptr()))
+        self.step_count = 0
+        return self._view(self._obs.clone())
+
+    def observe(self) -> torch.Tensor:
+        _lib.check(self.L.drl_env_observe(C.byref(self.struct), self._obs.data_ptr(), _lib.stream_ptr()))
+        return self._view(self._obs.clone())
+
+    def observe_padded(self) -> torch.Tensor:
+        _lib.check(self.L.drl_env_observe(C.byref(self.struct), self._obs.data_ptr(), _lib.stream_ptr()))
+        return self._obs
+
+    def set_state(self, state: torch.Tensor) -> torch.Tensor:
+        """Inject float64 states [N, 4] (parity tests teacher-force the oracle's states)."""
+        self.state.copy_(torch.as_tensor(state, dtype=torch.float64).reshape(self.num_envs, 4).t())
+        return self.observe()
+
+    def get_state(self) -> torch.Tensor:
+        return self.state.t().contiguous()
+
+    def step(self, action: torch.Tensor):
+        a = torch.as_tensor(action, device=self.device).reshape(self.num_envs).to(torch.int32).contiguous()
+        before = int(self.log.count.item()) if self.num_envs == 1 else None
+        _lib.check(self.L.drl_env_step(C.byref(self.struct), self.step_count, a.data_ptr(), self._obs.data_ptr(),
+                                       self._rew.data_ptr(), self._done.data_ptr(), C.byref(self.log.struct),
+                                       _lib.stream_ptr()))
+        self.step_count += 1
+        obs, rew, done = self._view(self._obs.clone()), self._rew.clone(), self._done.to(torch.bool)
+        info = {}
+        if self.num_envs == 1:
+            d = bool(done.item())
+            if d:
+                k = min(before, self.log.cap - 1)
+                info["episode"] = {"r": float(self.log.ret[k].item()), "l": int(self.log.len[k].item())}
+            return obs, float(rew.item()), d, info
+        return obs, rew, done, info
+
+    def close(self):
+        pass
+
+
+def make(env_id: str = "CartPole-v1", num_envs: int = 1, seed: int = 1, **kw) -> VecEnv:
+    """Counterpart of `gym.wrappers.RecordEpisodeStatistics(gym.make(env_id))` wrapped in `TorchWrapper`."""
+    return VecEnv(env_id, num_envs=num_envs, seed=seed, **kw)

@@ -1,0 +1,231 @@
+"""PPO rollout-and-update loop on the GPU -- the B200 counterpart of the script deep_rl/ppo.py.
+
+Hyper-parameter names and defaults are the reference's (ppo.py:62-76,83); `num_envs` and `hidden`
+are the two additions.  The loop keeps the shape of ppo.py:105-192:
+
+    for update in range(num_updates):
+        lr anneal                          ppo.py:107-108   (host scalar)
+        rollout of num_steps               ppo.py:110-141   drl_rollout        (1 launch)
+        GAE + returns (+ record packing)   ppo.py:144-151   drl_gae            (1 launch)
+        for epoch in range(update_epochs):
+            permutation                    ppo.py:155       drl_permutation + drl_adv_stats
+            for each minibatch:            ppo.py:156-192   drl_ppo_minibatch_grad
+                                                            [NCCL all-reduce of the flat gradient]
+                                                            drl_clip_adam
+
+Run as a script:  python -m deep_rl_b200.ppo [--num-envs N] [--total-timesteps K] ...
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib, dist as _dist
+from .agent import ActorCritic
+from .envs import VecEnv
+
+
+@dataclass
+class PPOConfig:
+    env_id: str = "CartPole-v1"
+    total_timesteps: int = 20_000
+    num_steps: int = 128
+    update_epochs: int = 4
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    learning_rate: float = 2.5e-4
+    clip_coef: float = 0.2
+    ent_coef: float = 0.01
+    vf_coef: float = 0.5
+    max_grad_norm: float = 0.5
+    seed: int = 1
+    # additions over the reference script
+    num_envs: int = 1            # environments per rank
+    hidden: int = 64
+    num_minibatches: int = 4     # reference: minibatch_size = num_steps // 4
+    anneal_lr: bool = True
+
+    @property
+    def batch_size(self) -> int:             # samples per rank per update
+        return self.num_envs * self.num_steps
+
+    @property
+    def minibatch_size(self) -> int:
+        return self.batch_size // self.num_minibatches
+
+    def num_updates(self, world: int = 1) -> int:
+        return self.total_timesteps // (self.batch_size * world)
+
+
+class PPOTrainer:
+    """Owns the device buffers of one rank and issues the kernels of one update."""
+
+    def __init__(self, cfg: PPOConfig, rank: int = 0, world: int = 1, device: Optional[torch.device] = None,
+                 agent: Optional[ActorCritic] = None):
+        _lib.require_cuda()
+        self.cfg, self.rank, self.world = cfg, int(rank), int(world)
+        self.L = _lib.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        N, T = cfg.num_envs, cfg.num_steps
+        self.env = VecEnv(cfg.env_id, num_envs=N, seed=cfg.seed, env_gid0=self.rank * N, device=self.device)
+        if agent is None:
+            torch.manual_seed(cfg.seed)      # same init draws on every rank (ppo.py:86,89)
+            agent = ActorCritic(self.env, hidden=cfg.hidden, device=self.device, sample_seed=cfg.seed)
+        self.agent = agent
+        self.net = agent.net
+        OP = self.env.obs_stride
+        dev = self.device
+        f32, u8 = torch.float32, torch.uint8
+        # storage, ppo.py:93-98, SoA [T+1][N]
+        self.observations = torch.zeros((T + 1, N, OP), dtype=f32, device=dev)
+        self.actions = torch.zeros((T + 1, N), dtype=u8, device=dev)
+        self.log_probs = torch.zeros((T + 1, N), dtype=f32, device=dev)
+        self.values = torch.zeros((T + 1, N), dtype=f32, device=dev)
+        self.rewards = torch.zeros((T + 1, N), dtype=f32, device=dev)
+        self.dones = torch.zeros((T + 1, N), dtype=u8, device=dev)
+        self.advantages = torch.zeros((T + 1, N), dtype=f32, device=dev)
+        self.returns = torch.zeros((T + 1, N), dtype=f32, device=dev)
+        self.buf = _lib.RolloutBufT(self.observations.data_ptr(), self.actions.data_ptr(), self.log_probs.data_ptr(),
+                                    self.values.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr())
+        B = cfg.batch_size
+        self.RW = self.L.drl_record_width(C.byref(self.net))
+        self.records = torch.zeros((B, self.RW), dtype=f32, device=dev)
+        self.idx = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.n_mb = (B + cfg.minibatch_size - 1) // cfg.minibatch_size
+        self.adv_stats = torch.zeros((self.n_mb, 2), dtype=f32, device=dev)
+        P = agent.flat_params.numel()
+        self.grad = torch.zeros(P, dtype=f32, device=dev)
+        self.exp_avg = torch.zeros(P, dtype=f32, device=dev)
+        self.exp_avg_sq = torch.zeros(P, dtype=f32, device=dev)
+        self.loss_terms = torch.zeros((cfg.update_epochs * self.n_mb, 8), dtype=f32, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=f32, device=dev)
+        self.ws_bytes = int(self.L.drl_workspace_bytes(C.byref(self.net)))
+        self.workspace = torch.zeros(self.ws_bytes, dtype=u8, device=dev)
+        self.coef = _lib.PpoCoefT(cfg.clip_coef, cfg.ent_coef, cfg.vf_coef)
+        self.adam_step = 0
+        self.update_idx = 0
+        self.global_step = 0       # env steps taken on this rank's envs x world (reference counter at N=1)
+        self.env.reset()           # ppo.py:101
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    def learning_rate(self, update: int, num_updates: int) -> float:
+        if not self.cfg.anneal_lr:
+            return self.cfg.learning_rate
+        return (1.0 - update / num_updates) * self.cfg.learning_rate      # ppo.py:107-108
+
+    def rollout(self) -> None:
+        """ppo.py:110-141 for all envs: one kernel launch."""
+        cfg = self.cfg
+        _lib.check(self.L.drl_rollout(C.byref(self.env.struct), C.byref(self.net), self.agent.packed.data_ptr(),
+                                      cfg.num_steps, self.env.step_count, C.byref(self.buf),
+                                      C.byref(self.env.log.struct), _lib.stream_ptr()))
+        self.env.step_count += cfg.num_steps
+        self.global_step += cfg.num_steps * cfg.num_envs * self.world
+        self.kernel_launches += 1
+
+    def compute_gae(self) -> None:
+        """ppo.py:144-151 (+ packs the per-sample records the update gathers)."""
+        cfg = self.cfg
+        _lib.check(self.L.drl_gae(C.byref(self.buf), C.byref(self.net), cfg.num_steps, cfg.num_envs, cfg.gamma,
+                                  cfg.gae_lambda, self.advantages.data_ptr(), self.returns.data_ptr(),
+                                  self.records.data_ptr(), _lib.stream_ptr()))
+        self.kernel_launches += 1
+
+    def optimize(self, lr: float) -> None:
+        """ppo.py:154-192."""
+        cfg, st = self.cfg, _lib.stream_ptr()
+        B, M = cfg.batch_size, cfg.minibatch_size
+        net = C.byref(self.net)
+        for epoch in range(cfg.update_epochs):
+            epoch_ctr = self.update_idx * cfg.update_epochs + epoch
+            _lib.check(self.L.drl_permutation(self.idx.data_ptr(), B, cfg.seed, epoch_ctr, self.rank, st))
+            _lib.check(self.L.drl_adv_stats(net, self.records.data_ptr(), self.idx.data_ptr(), B, M,
+                                            self.adv_stats.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, st))
+            self.kernel_launches += 2
+            for k in range(self.n_mb):
+                start = k * M
+                count = min(M, B - start)
+                row = epoch * self.n_mb + k
+                _lib.check(self.L.drl_ppo_minibatch_grad(
+                    net, self.agent.packed.data_ptr(), self.records.data_ptr(), self.idx.data_ptr(), start, count,
+                    self.adv_stats.data_ptr() + 8 * k, C.byref(self.coef), self.grad.data_ptr(),
+                    self.loss_terms.data_ptr() + 32 * row, self.workspace.data_ptr(), self.ws_bytes, st))
+                if self.world > 1:
+                    _dist.all_reduce_sum(self.grad)       # the only collective: NCCL over NVLink
+                self.adam_step += 1
+                _lib.check(self.L.drl_clip_adam(net, self.agent.flat_params.data_ptr(), self.grad.data_ptr(),
+                                                self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.adam_step, lr,
+                                                0.9, 0.999, 1e-5, cfg.max_grad_norm, 1.0 / self.world,
+                                                self.agent.packed.data_ptr(), self.grad_norm.data_ptr(), st))
+                self.kernel_launches += 3
+
+    def update(self, num_updates: Optional[int] = None) -> None:
+        """One full update (rollout + GAE + epochs), asynchronous: no host synchronisation."""
+        nu = num_updates if num_updates is not None else max(1, self.cfg.num_updates(self.world))
+        lr = self.learning_rate(self.update_idx, nu)
+        self.rollout()
+        self.compute_gae()
+        self.optimize(lr)
+        self.update_idx += 1
+        self.agent.mark_packed_current()
+
+    def metrics(self) -> Dict[str, float]:
+        """Device->host read of the last update's loss terms and the finished-episode log (synchronises)."""
+        lt = self.loss_terms[-1].tolist()
+        n, sum_ret, sum_len, entries = self.env.log.drain()
+        return {"loss": lt[0], "pg_loss": lt[1], "v_loss": lt[2], "entropy": lt[3], "approx_kl": lt[4],
+                "clipfrac": lt[5], "grad_norm": float(self.grad_norm.item()), "episodes": n,
+                "mean_return": (sum_ret / n) if n else float("nan"), "mean_length": (sum_len / n) if n else float("nan"),
+                "episode_log": entries}
+
+    def explained_variance(self) -> float:
+        """ppo.py:194-195 (computed over all T+1 slots like the reference)."""
+        y, r = self.values.flatten(), self.returns.flatten()
+        var_y = torch.var(y)
+        return float("nan") if float(var_y) == 0 else float(1 - torch.var(y - r) / var_y)
+
+
+def train(cfg: PPOConfig, quiet: bool = False, rank: int = 0, world: int = 1) -> PPOTrainer:
+    """The training loop of the reference script; prints its `global_step=..., episodic_return=...` lines."""
+    tr = PPOTrainer(cfg, rank=rank, world=world)
+    nu = cfg.num_updates(world)
+    per_vec_step = cfg.num_envs * world
+    for _ in range(nu):
+        tr.update(nu)
+        m = tr.metrics()
+        if not quiet and rank == 0:
+            if cfg.num_envs * world <= 16:
+                for step, env_gid, ret, _len in m["episode_log"]:
+                    print(f"global_step={step * per_vec_step + env_gid}, episodic_return={ret:.2f}")
+            elif m["episodes"]:
+                print(f"global_step={tr.global_step}, episodic_return={m['mean_return']:.2f} "
+                      f"(mean of {m['episodes']} episodes)")
+    return tr
+
+
+def main(argv=None) -> None:
+    p = argparse.ArgumentParser(description="PPO on device-resident classic-control envs (B200)")
+    d = PPOConfig()
+    p.add_argument("--env-id", default=d.env_id)
+    p.add_argument("--total-timesteps", type=int, default=d.total_timesteps)
+    p.add_argument("--num-steps", type=int, default=d.num_steps)
+    p.add_argument("--num-envs", type=int, default=d.num_envs)
+    p.add_argument("--update-epochs", type=int, default=d.update_epochs)
+    p.add_argument("--learning-rate", type=float, default=d.learning_rate)
+    p.add_argument("--seed", type=int, default=d.seed)
+    a = p.parse_args(argv)
+    rank, world = _dist.init_from_env()
+    cfg = PPOConfig(env_id=a.env_id, total_timesteps=a.total_timesteps, num_steps=a.num_steps, num_envs=a.num_envs,
+                    update_epochs=a.update_epochs, learning_rate=a.learning_rate, seed=a.seed)
+    train(cfg, rank=rank, world=world)
+    _dist.shutdown()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+/*
+ * drl_b200.h -- C ABI of libdrl_b200.so: the B200 (sm_100a) implementation of the PPO
+ * rollout-and-update hot path of qgallouedec/deep_rl `deep_rl/ppo.py`.
+ *
+ * The reference has no FFI of its own (it is a Python script); each entry point below replaces a
+ * span of that script, cited as ppo.py:LINES.  Conventions:
+ *   - every pointer is CALLER-OWNED DEVICE memory unless the name ends in `_host`; the library
+ *     never allocates, frees or retains device memory, and keeps no state between calls;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*, NULL = default stream)
+ *     and never synchronises with the host;
+ *   - return value 0 = ok, negative = error (drl_last_error() gives the message of the calling
+ *     thread's last failure); no C++ exception crosses this boundary;
+ *   - one host thread per device/stream; entry points are re-entrant across threads.
+ *
+ * Layouts (N = envs on this rank, T = num_steps, O = obs dim, OP = padded obs stride, A = actions):
+ *   rollout buffer planes are [T+1][N] with N contiguous, keeping the reference's one-slot shift
+ *   (ppo.py:93-98,113-141): rew[t+1], done[t+1] belong to act[t]; val[t] = V(obs[t]); obs is
+ *   [T+1][N][OP] float (OP = 4 CartPole, 8 Acrobot, pad lanes zero).
+ *   sample id s = t*N + n, 0 <= s < B = T*N.
+ */
+#ifndef DRL_B200_H
+#define DRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRL_ABI_VERSION 1
+
+enum { DRL_ENV_CARTPOLE = 0, DRL_ENV_ACROBOT = 1 };
+enum { DRL_OK = 0, DRL_ERR_ARG = -1, DRL_ERR_UNSUPPORTED = -2, DRL_ERR_CUDA = -3 };
+
+/* Batched environment: replaces gym.make + TimeLimit + RecordEpisodeStatistics + TorchWrapper
+ * (ppo.py:10-22,79-80) and the manual auto-reset of ppo.py:127-129, for N envs. */
+typedef struct {
+    int32_t  kind;               /* DRL_ENV_* */
+    int32_t  num_envs;           /* N on this rank */
+    uint64_t seed;               /* Philox key (ppo.py:83-84) */
+    uint32_t env_gid0;           /* global id of local env 0 (rank * N) -- Philox counter word */
+    int32_t  max_episode_steps;  /* TimeLimit, 500 for CartPole-v1 / Acrobot-v1 */
+    double*  state;              /* [4][N] float64, SoA (gym keeps float64 state) */
+    int32_t* elapsed;            /* [N] TimeLimit counter */
+    float*   ep_ret;             /* [N] running episode return (float32 like RecordEpisodeStatistics) */
+    int32_t* ep_len;             /* [N] running episode length */
+} drl_env_t;
+
+/* Finished-episode log: replaces info["episode"] + the print of ppo.py:130. All fields optional
+ * (pass a NULL drl_ep_log_t* to drop the log). */
+typedef struct {
+    uint32_t* count;     /* [1] episodes finished (atomic; may exceed cap, entries beyond cap dropped) */
+    double*   sum_ret;   /* [1] sum of finished returns */
+    double*   sum_len;   /* [1] sum of finished lengths */
+    float*    log_ret;   /* [cap] */
+    int32_t*  log_len;   /* [cap] */
+    uint32_t* log_env;   /* [cap] global env id */
+    uint64_t* log_step;  /* [cap] global step index (0-based) at which the episode ended */
+    uint32_t  cap;
+} drl_ep_log_t;
+
+/* Actor-critic shape (ppo.py:31-47): two separate tanh MLPs O->H->H->A and O->H->H->1. */
+typedef struct {
+    int32_t obs_dim;      /* O */
+    int32_t hidden;       /* H (64 supported) */
+    int32_t num_actions;  /* A */
+    int32_t obs_stride;   /* OP */
+} drl_net_t;
+
+typedef struct {
+    float*   obs;   /* [T+1][N][OP] */
+    uint8_t* act;   /* [T+1][N] */
+    float*   logp;  /* [T+1][N] */
+    float*   val;   /* [T+1][N] */
+    float*   rew;   /* [T+1][N] */
+    uint8_t* done;  /* [T+1][N] */
+} drl_rollout_buf_t;
+
+typedef struct {
+    float clip_coef;  /* ppo.py:72 */
+    float ent_coef;   /* ppo.py:73 */
+    float vf_coef;    /* ppo.py:74 */
+} drl_ppo_coef_t;
+
+int         drl_abi_version(void);
+const char* drl_last_error(void);
+
+/* ---- shapes ---- */
+int drl_env_obs_dim(int32_t kind);
+int drl_env_num_actions(int32_t kind);
+int drl_env_obs_stride(int32_t kind);
+/* canonical flat parameter count (state_dict order, ppo.py:34-47) and packed-layout float count */
+int64_t drl_param_count(const drl_net_t* net);
+int64_t drl_packed_count(const drl_net_t* net);
+/* sample-record width in floats (8 for O<=4, 16 otherwise) */
+int drl_record_width(const drl_net_t* net);
+/* bytes of zero-initialised scratch the update entry points need */
+size_t drl_workspace_bytes(const drl_net_t* net);
+
+/* ---- environment (ppo.py:17,21,79,101,127-129) ---- */
+int drl_env_reset(const drl_env_t* env, float* obs_out /*[N][OP]*/, void* stream);
+int drl_env_observe(const drl_env_t* env, float* obs_out /*[N][OP]*/, void* stream);
+int drl_env_step(const drl_env_t* env, uint64_t step, const int32_t* actions /*[N]*/, float* obs_out /*[N][OP]*/,
+                 float* rew_out /*[N]*/, uint8_t* done_out /*[N]*/, const drl_ep_log_t* log, void* stream);
+
+/* ---- model (ppo.py:49-59) ---- */
+/* canonical params -> kernel layout (transposed / lane-permuted copies staged to shared memory by TMA) */
+int drl_pack_params(const drl_net_t* net, const float* params, float* packed_out, void* stream);
+int drl_policy_forward(const drl_net_t* net, const float* packed, const float* obs /*[n][OP]*/, int64_t n,
+                       float* logits_out /*[n][A]*/, float* value_out /*[n]*/, void* stream);
+/* Categorical(logits).sample() + log_prob on the Philox stream (counter = env_gid0+i, step) */
+int drl_sample(const float* logits /*[n][A]*/, int64_t n, int32_t num_actions, uint64_t seed, uint32_t env_gid0,
+               uint64_t step, int32_t* act_out /*[n]*/, float* logp_out /*[n]*/, void* stream);
+
+/* ---- fused rollout, ppo.py:110-141: T x (actor+critic forward, sample, env step, stores) ---- */
+int drl_rollout(const drl_env_t* env, const drl_net_t* net, const float* packed, int32_t T, uint64_t step0,
+                const drl_rollout_buf_t* buf, const drl_ep_log_t* log, void* stream);
+
+/* ---- GAE + returns, ppo.py:144-151; optionally packs per-sample records for the update ----
+ * adv_out/ret_out are [T+1][N] (row T = 0 / val[T], as the reference leaves them).
+ * rec_out (nullable) is [T*N][RW]: obs[0..O), then at the last four words logp, adv, val, act(int32 bits). */
+int drl_gae(const drl_rollout_buf_t* buf, const drl_net_t* net, int32_t T, int32_t N, float gamma, float gae_lambda,
+            float* adv_out, float* ret_out, float* rec_out, void* stream);
+
+/* ---- minibatch permutation, ppo.py:155 ---- */
+int drl_permutation(uint32_t* idx_out /*[B]*/, uint32_t B, uint64_t seed, uint32_t epoch_ctr, uint32_t rank, void* stream);
+
+/* ---- per-minibatch advantage statistics (mean, unbiased std), ppo.py:169 ----
+ * stats_out [num_minibatches][2] float; minibatch k covers idx[k*mb_size, min(B,(k+1)*mb_size)). idx NULL = identity. */
+int drl_adv_stats(const drl_net_t* net, const float* rec, const uint32_t* idx, uint32_t B, uint32_t mb_size,
+                  float* stats_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- loss + backward of one minibatch, ppo.py:159-187 + backward of ppo.py:190 ----
+ * grad_out [P] canonical layout, mean over the mb_count samples; loss_terms_out[8] =
+ * {loss, pg_loss, v_loss, entropy, approx_kl, clipfrac, 0, 0}. */
+int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const float* rec, const uint32_t* idx,
+                           uint32_t mb_start, uint32_t mb_count, const float* adv_stats /*[2] mean,std*/,
+                           const drl_ppo_coef_t* coef, float* grad_out, float* loss_terms_out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- clip_grad_norm_ + Adam, ppo.py:191-192 (after the gradient all-reduce) ----
+ * grad is multiplied by grad_scale (1/world) first; `step` is the 1-based Adam step of this call.
+ * packed_out (nullable) receives the refreshed kernel layout; norm_out (nullable, [1]) the pre-clip norm. */
+int drl_clip_adam(const drl_net_t* net, float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
+                  int64_t step, double lr, double beta1, double beta2, double eps, double max_grad_norm,
+                  double grad_scale, float* packed_out, float* norm_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRL_B200_H */

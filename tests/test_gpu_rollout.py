@@ -1,0 +1,188 @@
+"""GPU parity tests of the fused rollout kernel and of whole PPO updates (deep_rl/ppo.py:105-192)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import clib, ppo_oracle as po  # noqa: E402
+
+
+def _check_rollout(env_id, N, T, seed, sub=None, rounds=2):
+    """Teacher-forced check of drl_rollout against the oracle:
+       * oracle forward on the kernel's stored obs[t] must reproduce val[t] and the log-prob,
+       * the oracle sampler fed the oracle logits must pick the kernel's action (bit-exact unless the
+         uniform sits within 2e-6 of a CDF edge, where a 1e-6 logit difference may legally flip it),
+       * the oracle env driven by the kernel's actions must reproduce obs/rew/done (<= 1e-6 per step),
+         auto-resets (Philox reset draws) and the episode log included."""
+    import deep_rl_b200 as drl
+    if sub is not None:
+        os.environ["DRL_ROLLOUT_SUB"] = str(sub)
+    try:
+        cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=seed)
+        tr = drl.PPOTrainer(cfg)
+        O, A = tr.env.obs_dim, tr.env.num_actions
+        ora = clib.OracleVecEnv(env_id, N, seed=seed)
+        obs0 = ora.reset()
+        flat = tr.agent.flat_params.cpu()
+        mism = 0
+        for rnd in range(rounds):
+            tr.rollout()
+            torch.cuda.synchronize()
+            obs = tr.observations.cpu().numpy()[:, :, :O]
+            act = tr.actions.cpu().numpy().astype(np.int32)
+            logp, val = tr.log_probs.cpu().numpy(), tr.values.cpu().numpy()
+            rew, done = tr.rewards.cpu().numpy(), tr.dones.cpu().numpy()
+            np.testing.assert_allclose(obs[0], obs0, rtol=0, atol=1e-7)
+            fin = []
+            for t in range(T + 1):
+                with torch.no_grad():
+                    logits, v = po.mlp_forward(flat, torch.from_numpy(np.ascontiguousarray(obs[t])), O, 64, A)
+                np.testing.assert_allclose(val[t], v.numpy(), rtol=0, atol=2e-5, err_msg=f"value t={t}")
+                if t == T:
+                    break
+                step = ora.step_count
+                wa, _ = clib.sample(logits.numpy(), seed, 0, step)
+                lsm = torch.log_softmax(logits, -1).numpy()
+                np.testing.assert_allclose(logp[t], lsm[np.arange(N), act[t]], rtol=0, atol=2e-5, err_msg=f"logp t={t}")
+                bad = np.nonzero(wa != act[t])[0]
+                for i in bad:   # only allowed within rounding distance of a CDF edge
+                    u = clib.action_uniform(seed, int(i), step)
+                    cdf = np.cumsum(np.exp(lsm[i].astype(np.float64)))
+                    assert np.min(np.abs(cdf[:-1] - u)) < 2e-6, f"action mismatch env {i} t={t}: u={u} cdf={cdf}"
+                    mism += 1
+                o, r, d, info = ora.step(act[t])
+                np.testing.assert_allclose(obs[t + 1], o, rtol=0, atol=1e-6, err_msg=f"obs t={t + 1}")
+                assert np.array_equal(rew[t + 1], r) and np.array_equal(done[t + 1], d), f"rew/done t={t + 1}"
+                for i in np.nonzero(d)[0]:
+                    fin.append((step, int(i), float(info["final_return"][i]), int(info["final_length"][i])))
+            obs0 = obs[T]
+            cnt, sum_ret, sum_len, entries = tr.env.log.drain()
+            assert cnt == len(fin)
+            assert entries == sorted(fin)
+            np.testing.assert_allclose(tr.env.get_state().cpu().numpy(), ora.state, rtol=0, atol=1e-9)
+        assert mism <= 1
+        return tr
+    finally:
+        os.environ.pop("DRL_ROLLOUT_SUB", None)
+
+
+@pytest.mark.parametrize("env_id,N,T,sub", [
+    ("CartPole-v1", 1, 128, None),        # the reference's own shape
+    ("CartPole-v1", 13, 40, None),        # ragged: not a multiple of the 8-env tile
+    ("CartPole-v1", 256, 64, None),
+    ("CartPole-v1", 100, 48, 2),
+    ("CartPole-v1", 300, 32, 4),
+    ("Acrobot-v1", 40, 48, None),
+    ("Acrobot-v1", 70, 24, 4),
+])
+def test_rollout_vs_oracle(env_id, N, T, sub):
+    _check_rollout(env_id, N, T, seed=3, sub=sub)
+
+
+def test_rollout_world_size_invariance():
+    """Global env id feeds the Philox counter: rank 1 of a 2-rank job reproduces envs [N, 2N) of a 1-rank job."""
+    import deep_rl_b200 as drl
+    T, N = 32, 24
+    full = drl.PPOTrainer(drl.PPOConfig(num_envs=2 * N, num_steps=T, seed=5))
+    full.rollout()
+    half = drl.PPOTrainer(drl.PPOConfig(num_envs=N, num_steps=T, seed=5), rank=1, world=2)
+    half.rollout()
+    torch.cuda.synchronize()
+    for name in ("observations", "actions", "log_probs", "values", "rewards", "dones"):
+        a, b = getattr(full, name)[:, N:], getattr(half, name)
+        assert torch.equal(a, b), name
+
+
+def _oracle_update(tr, nu):
+    """One whole update on the CPU from the trainer's current state: GAE (C oracle), then the 16 minibatch steps
+    with torch autograd + torch.optim.Adam semantics, using the oracle permutation."""
+    cfg = tr.cfg
+    O, A, N, T = tr.env.obs_dim, tr.env.num_actions, cfg.num_envs, cfg.num_steps
+    B, M = cfg.batch_size, cfg.minibatch_size
+    obs = tr.observations.cpu().numpy()[:T, :, :O].reshape(B, O)
+    act = tr.actions.cpu().numpy()[:T].reshape(B)
+    logp = tr.log_probs.cpu().numpy()[:T].reshape(B)
+    val = tr.values.cpu().numpy()
+    adv, ret = clib.gae(tr.rewards.cpu().numpy(), tr.dones.cpu().numpy().astype(np.float32), val, cfg.gamma, cfg.gae_lambda)
+    return obs, act, logp, val[:T].reshape(B), adv, ret, B, M
+
+
+@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 1, 128), ("CartPole-v1", 64, 32), ("Acrobot-v1", 24, 64)])
+def test_full_update_vs_oracle(env_id, N, T):
+    """rollout (GPU) -> [GAE, permutation, statistics, 16 x (loss+backward, clip, Adam)] on GPU vs the CPU oracle
+    fed the same rollout buffers."""
+    import deep_rl_b200 as drl
+    cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=2, total_timesteps=N * T * 10)
+    tr = drl.PPOTrainer(cfg)
+    nu = cfg.num_updates()
+    for upd in range(2):
+        params0 = tr.agent.flat_params.cpu().numpy().copy()
+        m0, v0 = tr.exp_avg.cpu().numpy().copy(), tr.exp_avg_sq.cpu().numpy().copy()
+        step0 = tr.adam_step
+        tr.update(nu)
+        torch.cuda.synchronize()
+        obs, act, logp, val, adv, ret, B, M = _oracle_update(tr, nu)
+        assert np.array_equal(tr.advantages.cpu().numpy(), adv) and np.array_equal(tr.returns.cpu().numpy(), ret)
+        lr = (1.0 - upd / nu) * cfg.learning_rate
+        O, A = tr.env.obs_dim, tr.env.num_actions
+        p, m, v, k = params0, m0, v0, step0
+        terms_all = tr.loss_terms.cpu().numpy()
+        for epoch in range(cfg.update_epochs):
+            idx = clib.permutation(B, cfg.seed, upd * cfg.update_epochs + epoch, 0).astype(np.int64)
+            for j in range(4):
+                sel = idx[j * M:(j + 1) * M]
+                terms, grad = po.minibatch_loss_and_grad(p, obs[sel], act[sel], logp[sel], adv[:T].reshape(B)[sel],
+                                                         ret[:T].reshape(B)[sel], val[sel], O, 64, A)
+                k += 1
+                p, m, v, _ = po.clip_adam(p, grad, m, v, k, lr)
+                np.testing.assert_allclose(terms_all[epoch * 4 + j, :4], terms, rtol=1e-3, atol=2e-5,
+                                           err_msg=f"update {upd} epoch {epoch} mb {j}")
+        # Adam normalises the step, so tiny gradient differences can move a weight by O(lr * 1e-3)
+        np.testing.assert_allclose(tr.agent.flat_params.cpu().numpy(), p, rtol=0, atol=2e-5)
+        assert tr.adam_step == k
+    assert abs(tr.explained_variance()) < 10
+
+
+def test_reference_shape_learning_curve():
+    """The reference configuration (1 env, 128 steps, 20k timesteps, seed 1) must learn like the reference does
+    (golden: mean return of the first 20 episodes 27.8 -> last 20 episodes 217.1)."""
+    import deep_rl_b200 as drl
+    best = 0.0
+    for seed in (1, 2, 3):
+        cfg = drl.PPOConfig(seed=seed)
+        tr = drl.PPOTrainer(cfg)
+        eps = []
+        for _ in range(cfg.num_updates()):
+            tr.update()
+            eps += [e[2] for e in tr.metrics()["episode_log"]]
+        first, last = float(np.mean(eps[:20])), float(np.mean(eps[-20:]))
+        assert first < 60
+        best = max(best, last)
+    assert best > 120, best
+
+
+def test_many_envs_learns_cartpole():
+    import deep_rl_b200 as drl
+    cfg = drl.PPOConfig(num_envs=512, num_steps=128, total_timesteps=512 * 128 * 100, seed=1)
+    tr = drl.PPOTrainer(cfg)
+    rets = []
+    for _ in range(cfg.num_updates()):
+        tr.update()
+        m = tr.metrics()
+        if m["episodes"]:
+            rets.append(m["mean_return"])
+    assert rets[0] < 40 and max(rets[-5:]) > 150, rets
+
+
+def test_train_prints_reference_format(capsys):
+    import deep_rl_b200 as drl
+    drl.train(drl.PPOConfig(total_timesteps=1024, seed=1))
+    out = capsys.readouterr().out.strip().splitlines()
+    assert len(out) > 10
+    import re
+    assert all(re.fullmatch(r"global_step=\d+, episodic_return=\d+\.\d\d", ln) for ln in out)
+    steps = [int(ln.split(",")[0].split("=")[1]) for ln in out]
+    assert steps == sorted(steps) and steps[-1] < 1024
