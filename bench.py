@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- PPO env-steps/sec (rollout + update) on CartPole-v1, the metric BASELINE.json names.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...             # the reference's CPU implementation (port)
+
+A "step" is one PPO update = one rollout of T env steps on every env, GAE, and 4 epochs x 4 minibatch
+optimizer steps (deep_rl/ppo.py:105-192).  Workloads (BASELINE.json configs):
+    N = 1 : C2  CartPole-v1, 4096 envs x 128 steps, 64-wide MLP
+    N > 1 : C3  CartPole-v1, 65,536 envs per GPU x 128 steps, env-sharded, NCCL gradient all-reduce
+`value` times the K updates with everything resident in HBM (per-update CUDA events, L2 flushed between
+updates outside the events, max over ranks); `e2e` drives the same K updates through the public API with
+a host round trip every update (metrics read back device->host, host-side logging logic).  Rank 0 prints
+ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_FWD = {("CartPole-v1", 64): 17_792, ("Acrobot-v1", 64): 18_432}   # forward FLOPs per sample
+BYTES_PER_ENV_STEP = {"CartPole-v1": 195, "Acrobot-v1": 235}
+GRAD_BYTES_PER_SAMPLE = {"CartPole-v1": 37, "Acrobot-v1": 45}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation (oracle port; /root/reference and gym do not exist
+# on the GPU box), one independent single-threaded process per host core.
+# ------------------------------------------------------------------------------------------------
+def _port_worker(seed: int, updates: int, warm: int, q):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import ppo_port as pp
+    cfg = pp.PortConfig(seed=seed)
+    pp.run(cfg, max_updates=max(1, warm))
+    t0 = time.perf_counter()
+    tr = pp.run(cfg, max_updates=updates)
+    q.put((tr.env_steps, time.perf_counter() - t0))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs_n = max(1, min(cores, 64))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    t0 = time.perf_counter()
+    procs = [ctx.Process(target=_port_worker, args=(i + 1, args.steps, args.warmup, q)) for i in range(procs_n)]
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    value = steps / slowest
+    line = {
+        "impl": "reference", "metric": "PPO env-steps/sec (rollout+update) CartPole-v1", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * slowest / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "reference ppo.py shape: CartPole-v1, 1 env x 128 steps per update, 64-wide MLP, "
+                               f"{procs_n} independent single-threaded processes (the script is single-threaded)",
+                   "env_id": "CartPole-v1", "num_steps": 128, "hidden": 64},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": procs_n, "kind": "port",
+                         "sample": f"{args.steps} updates x 128 env-steps per process after {max(1, args.warmup)} warm-up update(s); "
+                                   f"per-process {value / procs_n:.0f} env-steps/s; host has {cores} cores; wall {wall:.1f}s"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    from deep_rl_b200 import PPOConfig, PPOTrainer, dist
+
+    rank, world = dist.init_from_env()
+    if world != args.gpus and rank == 0:
+        print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    envs = args.envs_per_gpu if args.envs_per_gpu else (4096 if world == 1 else 65_536)
+    T = args.num_steps
+    workload = ("C2: PPO CartPole-v1, 4096 envs x 128 steps, 64-wide MLP, 1xB200" if (world == 1 and envs == 4096 and T == 128 and args.env_id == "CartPole-v1")
+                else f"C3: PPO CartPole-v1, 65,536 envs/GPU x 128 steps env-sharded across {world} B200, NCCL gradient all-reduce"
+                if (envs == 65_536 and T == 128 and args.env_id == "CartPole-v1") else f"custom: {args.env_id}, {envs} envs/GPU x {T} steps")
+    total_updates = args.warmup + 2 * args.steps + 8
+    cfg = PPOConfig(env_id=args.env_id, num_envs=envs, num_steps=T, total_timesteps=envs * T * world * total_updates, seed=1)
+    tr = PPOTrainer(cfg, rank=rank, world=world, device=dev)
+    nu = cfg.num_updates(world)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    for _ in range(max(3, args.warmup)):
+        tr.update(nu)
+    tr.metrics()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing: per-update CUDA events, L2 flushed between updates ----
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    tr.timing = True
+    tr.phase_events.clear()
+    launches0 = tr.kernel_launches
+    evs = []
+    dist.barrier()
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tr.update(nu)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = tr.kernel_launches - launches0
+    phases = tr.phase_ms()
+    tr.timing = False
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    dev_ms = dist.all_reduce_max(dev_ms, dev)
+    steps_per_update = envs * T * world
+    value = steps_per_update * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the public API: update + host round trip every update ----
+    tr.metrics()
+    dist.barrier()
+    torch.cuda.synchronize()
+    d2h = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tr.update(nu)
+        m = tr.metrics()                       # D2H: loss terms, grad norm, episode count/sums/log entries
+        d2h += 32 + 4 + 4 + 16 + 20 * min(m["episodes"], tr.env.log.cap)
+        _ = (m["mean_return"], m["loss"])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_s = dist.all_reduce_max(e2e_s, dev)
+    e2e_value = steps_per_update * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (ppo_grad + its fixed-order reduce) ----
+    peaks = load_peaks()
+    F = F_FWD[(args.env_id, 64)]
+    M = cfg.minibatch_size
+    g = phases.get("minibatch_grad", {"mean_ms": float("nan"), "total_ms": 0.0})
+    flops_per_launch = 3 * F * M
+    achieved_tf = flops_per_launch / (g["mean_ms"] * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"ppo_grad_kernel@{M}")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "ppo_grad_kernel (+grad_reduce_kernel)", "bound": "tensor", "achieved": achieved_tf,
+                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops_sustained"],
+                "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "flops_per_launch": flops_per_launch, "launch_ms": g["mean_ms"],
+                "note": "FP32 CUDA-core (FFMA) path in this round; the tensor-pipe peak is the roof the tcgen05 path will be held to",
+                "hbm": {"achieved_gbs": GRAD_BYTES_PER_SAMPLE[args.env_id] * M / (g["mean_ms"] * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"]},
+                "end_to_end": {"hbm_frac": value * BYTES_PER_ENV_STEP[args.env_id] / world / 1e9 / peaks["hbm_gbs"],
+                               "tensor_frac": value * 13 * F / world / 1e12 / peaks["bf16_tflops_sustained"]},
+                "share_of_step": g["total_ms"] / max(1e-9, sum(a.elapsed_time(b) for a, b in evs))}
+
+    if rank != 0:
+        dist.shutdown()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import ppo_port as pp
+        import torch as _t
+        _t.set_num_threads(1)
+        r = pp.time_port(args.cpu_seconds)
+        cpu_baseline = {"value": r["steps_per_s"], "unit": "env-steps/s", "cores": 1, "kind": "port",
+                        "sample": f"{r['updates']} updates x 128 env-steps of the single-env CPU port of ppo.py "
+                                  f"({r['seconds']:.1f}s, single-threaded like the reference; host has {os.cpu_count()} cores)"}
+
+    line = {
+        "metric": "PPO env-steps/sec (rollout+update) CartPole-v1", "value": value, "unit": "env-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "env_id": args.env_id, "envs_per_gpu": envs, "num_steps": T, "hidden": 64,
+                   "minibatch_size": M, "update_epochs": cfg.update_epochs, "optimizer_steps_per_update": cfg.update_epochs * tr.n_mb,
+                   "parallelism": f"env-sharded x{world}", "l2": "flushed between updates (256 MiB memset outside the timed events); "
+                   "every update regenerates its own rollout data"},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / args.steps,
+                "note": "public API PPOTrainer.update()+metrics() with a host sync every update; the environments live on the "
+                        "device, so the only per-update host inputs are kernel arguments (no tensor H2D)"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "phases_ms_per_update": {k: v["total_ms"] / args.steps for k, v in phases.items()},
+    }
+    print(json.dumps(line), flush=True)
+    dist.shutdown()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=0)
+    ap.add_argument("--num-steps", type=int, default=128)
+    ap.add_argument("--env-id", default="CartPole-v1")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,26 @@ class PPOConfig:
         return self.total_timesteps // (self.batch_size * world)
 
 
+class _Phase:
+    """CUDA-event bracket around one phase of the update (only when trainer.timing is on)."""
+
+    def __init__(self, tr: "PPOTrainer", name: str):
+        self.tr, self.name = tr, name
+
+    def __enter__(self):
+        if self.tr.timing:
+            self.t0 = torch.cuda.Event(enable_timing=True)
+            self.t1 = torch.cuda.Event(enable_timing=True)
+            self.t0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.tr.timing:
+            self.t1.record()
+            self.tr.phase_events.setdefault(self.name, []).append((self.t0, self.t1))
+        return False
+
+
 class PPOTrainer:
     """Owns the device buffers of one rank and issues the kernels of one update."""
 
@@ -112,6 +132,17 @@ class PPOTrainer:
         self.global_step = 0       # env steps taken on this rank's envs x world (reference counter at N=1)
         self.env.reset()           # ppo.py:101
         self.kernel_launches = 0
+        self.timing = False        # record CUDA events around each phase (bench.py)
+        self.phase_events: Dict[str, list] = {}
+
+    def phase_ms(self) -> Dict[str, Dict[str, float]]:
+        """Per-phase device time from the recorded events: {phase: {calls, total_ms, mean_ms}} (synchronises)."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, evs in self.phase_events.items():
+            ms = [a.elapsed_time(b) for a, b in evs]
+            out[name] = {"calls": len(ms), "total_ms": float(sum(ms)), "mean_ms": float(sum(ms) / max(1, len(ms)))}
+        return out
 
     # ------------------------------------------------------------------------------------------
     def learning_rate(self, update: int, num_updates: int) -> float:
@@ -122,9 +153,10 @@ class PPOTrainer:
     def rollout(self) -> None:
         """ppo.py:110-141 for all envs: one kernel launch."""
         cfg = self.cfg
-        _lib.check(self.L.drl_rollout(C.byref(self.env.struct), C.byref(self.net), self.agent.packed.data_ptr(),
-                                      cfg.num_steps, self.env.step_count, C.byref(self.buf),
-                                      C.byref(self.env.log.struct), _lib.stream_ptr()))
+        with _Phase(self, "rollout"):
+            _lib.check(self.L.drl_rollout(C.byref(self.env.struct), C.byref(self.net), self.agent.packed.data_ptr(),
+                                          cfg.num_steps, self.env.step_count, C.byref(self.buf),
+                                          C.byref(self.env.log.struct), _lib.stream_ptr()))
         self.env.step_count += cfg.num_steps
         self.global_step += cfg.num_steps * cfg.num_envs * self.world
         self.kernel_launches += 1
@@ -132,9 +164,10 @@ class PPOTrainer:
     def compute_gae(self) -> None:
         """ppo.py:144-151 (+ packs the per-sample records the update gathers)."""
         cfg = self.cfg
-        _lib.check(self.L.drl_gae(C.byref(self.buf), C.byref(self.net), cfg.num_steps, cfg.num_envs, cfg.gamma,
-                                  cfg.gae_lambda, self.advantages.data_ptr(), self.returns.data_ptr(),
-                                  self.records.data_ptr(), _lib.stream_ptr()))
+        with _Phase(self, "gae"):
+            _lib.check(self.L.drl_gae(C.byref(self.buf), C.byref(self.net), cfg.num_steps, cfg.num_envs, cfg.gamma,
+                                      cfg.gae_lambda, self.advantages.data_ptr(), self.returns.data_ptr(),
+                                      self.records.data_ptr(), _lib.stream_ptr()))
         self.kernel_launches += 1
 
     def optimize(self, lr: float) -> None:
@@ -144,25 +177,30 @@ class PPOTrainer:
         net = C.byref(self.net)
         for epoch in range(cfg.update_epochs):
             epoch_ctr = self.update_idx * cfg.update_epochs + epoch
-            _lib.check(self.L.drl_permutation(self.idx.data_ptr(), B, cfg.seed, epoch_ctr, self.rank, st))
-            _lib.check(self.L.drl_adv_stats(net, self.records.data_ptr(), self.idx.data_ptr(), B, M,
-                                            self.adv_stats.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, st))
+            with _Phase(self, "permutation"):
+                _lib.check(self.L.drl_permutation(self.idx.data_ptr(), B, cfg.seed, epoch_ctr, self.rank, st))
+            with _Phase(self, "adv_stats"):
+                _lib.check(self.L.drl_adv_stats(net, self.records.data_ptr(), self.idx.data_ptr(), B, M,
+                                                self.adv_stats.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, st))
             self.kernel_launches += 2
             for k in range(self.n_mb):
                 start = k * M
                 count = min(M, B - start)
                 row = epoch * self.n_mb + k
-                _lib.check(self.L.drl_ppo_minibatch_grad(
-                    net, self.agent.packed.data_ptr(), self.records.data_ptr(), self.idx.data_ptr(), start, count,
-                    self.adv_stats.data_ptr() + 8 * k, C.byref(self.coef), self.grad.data_ptr(),
-                    self.loss_terms.data_ptr() + 32 * row, self.workspace.data_ptr(), self.ws_bytes, st))
+                with _Phase(self, "minibatch_grad"):
+                    _lib.check(self.L.drl_ppo_minibatch_grad(
+                        net, self.agent.packed.data_ptr(), self.records.data_ptr(), self.idx.data_ptr(), start, count,
+                        self.adv_stats.data_ptr() + 8 * k, C.byref(self.coef), self.grad.data_ptr(),
+                        self.loss_terms.data_ptr() + 32 * row, self.workspace.data_ptr(), self.ws_bytes, st))
                 if self.world > 1:
-                    _dist.all_reduce_sum(self.grad)       # the only collective: NCCL over NVLink
+                    with _Phase(self, "allreduce"):
+                        _dist.all_reduce_sum(self.grad)       # the only collective: NCCL over NVLink
                 self.adam_step += 1
-                _lib.check(self.L.drl_clip_adam(net, self.agent.flat_params.data_ptr(), self.grad.data_ptr(),
-                                                self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.adam_step, lr,
-                                                0.9, 0.999, 1e-5, cfg.max_grad_norm, 1.0 / self.world,
-                                                self.agent.packed.data_ptr(), self.grad_norm.data_ptr(), st))
+                with _Phase(self, "clip_adam"):
+                    _lib.check(self.L.drl_clip_adam(net, self.agent.flat_params.data_ptr(), self.grad.data_ptr(),
+                                                    self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.adam_step, lr,
+                                                    0.9, 0.999, 1e-5, cfg.max_grad_norm, 1.0 / self.world,
+                                                    self.agent.packed.data_ptr(), self.grad_norm.data_ptr(), st))
                 self.kernel_launches += 3
 
     def update(self, num_updates: Optional[int] = None) -> None:
