@@ -158,7 +158,12 @@ __global__ void __launch_bounds__(GT, 1) ppo_grad_kernel(GradArgs g) {
                     const float onehot = a == act ? 1.0f : 0.0f;
                     dl[a] = inv_m * (dpg * (onehot - p[a]) + g.ent_coef * p[a] * (lp[a] + ent));
                 }
-                dv = vu >= vcl ? g.vf_coef * vd * inv_m : 0.0f;
+                // d max(vu, vcl)/dv, torch semantics: the clipped branch passes gradient only inside the
+                // clamp range; an exact tie splits evenly between the two branches.
+                const float vdiff = v - val_old;
+                const float gcl = (vdiff >= -g.clip_coef && vdiff <= g.clip_coef) ? vcd : 0.0f;
+                const float gv = vu > vcl ? vd : (vcl > vu ? gcl : 0.5f * (vd + gcl));
+                dv = g.vf_coef * gv * inv_m;
             }
             *reinterpret_cast<float4*>(dout_s + lane * 4) = make_float4(dl[0], dl[1], dl[2], dl[3]);
             *reinterpret_cast<float4*>(dout_s + (TILE + lane) * 4) = make_float4(dv, 0.f, 0.f, 0.f);
@@ -354,31 +359,55 @@ __global__ void __launch_bounds__(GT, 1) ppo_grad_kernel(GradArgs g) {
     }
 }
 
-// Sum the per-CTA partials in a fixed order (deterministic) and finish the loss terms.
+// Sum the per-CTA partials in a fixed order (deterministic) and finish the loss terms.  blockDim = (32, 8):
+// thread (x, y) folds partials y, y+8, ... of parameter p with independent loads in flight, then the 8
+// slices are folded through shared memory in slice order.
 __global__ void __launch_bounds__(256) grad_reduce_kernel(const float* __restrict__ grad_part, const float* __restrict__ loss_part,
                                                            int nparts, int ppad, int P, uint32_t mb_count, float ent_coef,
                                                            float vf_coef, float* __restrict__ grad_out,
                                                            float* __restrict__ loss_terms_out) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float sh[8][33];
+    const int p = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.0f;
     if (p < P) {
-        float s = 0.0f;
-        for (int c = 0; c < nparts; ++c) s += grad_part[(size_t)c * ppad + p];
-        grad_out[p] = s;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int c = threadIdx.y;
+        for (; c + 24 < nparts; c += 32) {
+            const float v0 = __ldcg(grad_part + (size_t)c * ppad + p);
+            const float v1 = __ldcg(grad_part + (size_t)(c + 8) * ppad + p);
+            const float v2 = __ldcg(grad_part + (size_t)(c + 16) * ppad + p);
+            const float v3 = __ldcg(grad_part + (size_t)(c + 24) * ppad + p);
+            a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+        }
+        for (; c < nparts; c += 8) a0 += __ldcg(grad_part + (size_t)c * ppad + p);
+        s = (a0 + a1) + (a2 + a3);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && loss_terms_out != nullptr) {
-        float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < nparts; ++c)
-            for (int k = 0; k < 5; ++k) t[k] += loss_part[c * LOSS_TERMS + k];
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && p < P) {
+        float t = sh[0][threadIdx.x];
+#pragma unroll
+        for (int y = 1; y < 8; ++y) t += sh[y][threadIdx.x];
+        grad_out[p] = t;
+    }
+    if (blockIdx.x == 0 && threadIdx.y == 1 && threadIdx.x < 5 && loss_terms_out != nullptr) {
+        // lanes 0-4 of warp 1 each fold one loss term over the CTAs, lane 0 then finishes the terms
+        float t = 0.f;
+        for (int c = 0; c < nparts; ++c) t += __ldcg(loss_part + c * LOSS_TERMS + threadIdx.x);
         const float inv = 1.0f / (float)mb_count;
-        const float pg = t[0] * inv, vl = 0.5f * t[1] * inv, en = t[2] * inv;
-        loss_terms_out[0] = pg - ent_coef * en + vl * vf_coef;
-        loss_terms_out[1] = pg;
-        loss_terms_out[2] = vl;
-        loss_terms_out[3] = en;
-        loss_terms_out[4] = t[3] * inv;
-        loss_terms_out[5] = t[4] * inv;
-        loss_terms_out[6] = 0.0f;
-        loss_terms_out[7] = 0.0f;
+        const float t0 = __shfl_sync(0x1fu, t, 0), t1 = __shfl_sync(0x1fu, t, 1), t2 = __shfl_sync(0x1fu, t, 2);
+        const float t3 = __shfl_sync(0x1fu, t, 3), t4 = __shfl_sync(0x1fu, t, 4);
+        if (threadIdx.x == 0) {
+            const float pg = t0 * inv, vl = 0.5f * t1 * inv, en = t2 * inv;
+            loss_terms_out[0] = pg - ent_coef * en + vl * vf_coef;
+            loss_terms_out[1] = pg;
+            loss_terms_out[2] = vl;
+            loss_terms_out[3] = en;
+            loss_terms_out[4] = t3 * inv;
+            loss_terms_out[5] = t4 * inv;
+            loss_terms_out[6] = 0.0f;
+            loss_terms_out[7] = 0.0f;
+        }
     }
 }
 
@@ -395,9 +424,22 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(AdamArgs a) {
     __shared__ double sh[8];
     __shared__ float s_coef;
     double ss = 0.0;
-    for (int i = threadIdx.x; i < a.P; i += blockDim.x) {
-        const double gv = (double)(a.grad[i] * a.grad_scale);
-        ss = fma(gv, gv, ss);
+    {   // 16-byte loads, four independent partial sums per thread: the whole gradient is read in ~9 round trips
+        const float4* g4 = reinterpret_cast<const float4*>(a.grad);
+        const int n4 = a.P / 4;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < n4; i += 256) {
+            const float4 q = __ldcg(g4 + i);
+            const double x = (double)(q.x * a.grad_scale), y = (double)(q.y * a.grad_scale);
+            const double z = (double)(q.z * a.grad_scale), w = (double)(q.w * a.grad_scale);
+            s0 = fma(x, x, s0); s1 = fma(y, y, s1); s2 = fma(z, z, s2); s3 = fma(w, w, s3);
+        }
+        ss = (s0 + s1) + (s2 + s3);
+        for (int i = n4 * 4 + threadIdx.x; i < a.P; i += 256) {
+            const double gv = (double)(a.grad[i] * a.grad_scale);
+            ss = fma(gv, gv, ss);
+        }
     }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
@@ -434,7 +476,7 @@ int launch_grad(const GradArgs& g, int P, float* grad_out, float* loss_terms_out
     if ((uint32_t)grid > ntiles) grid = (int)ntiles;
     ppo_grad_kernel<O, A, OP, RW><<<grid, GT, smem, st>>>(g);
     DRL_LAUNCH_CHECK("ppo_grad_kernel");
-    grad_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(g.grad_part, g.loss_part, grid, g.ppad, P, g.mb_count, g.ent_coef,
+    grad_reduce_kernel<<<(P + 31) / 32, dim3(32, 8), 0, st>>>(g.grad_part, g.loss_part, grid, g.ppad, P, g.mb_count, g.ent_coef,
                                                        g.vf_coef, grad_out, loss_terms_out);
     DRL_LAUNCH_CHECK("grad_reduce_kernel");
     return DRL_OK;

@@ -26,8 +26,12 @@ class EpisodeLog:
 
     def __init__(self, cap: int, device):
         self.cap = int(cap)
-        self.count = torch.zeros(1, dtype=torch.int32, device=device)
-        self.sums = torch.zeros(2, dtype=torch.float64, device=device)      # sum_ret, sum_len
+        # count (int32 @0) and the two float64 sums (@8, @16) share one 24-byte buffer: one fill clears them,
+        # one 24-byte device->host copy reads them.
+        self._hdr = torch.zeros(24, dtype=torch.uint8, device=device)
+        self.count = self._hdr[0:4].view(torch.int32)
+        self.sums = self._hdr[8:24].view(torch.float64)      # sum_ret, sum_len
+        self._hdr_host = torch.zeros(24, dtype=torch.uint8).pin_memory()
         self.ret = torch.zeros(self.cap, dtype=torch.float32, device=device)
         self.len = torch.zeros(self.cap, dtype=torch.int32, device=device)
         self.env = torch.zeros(self.cap, dtype=torch.int32, device=device)
@@ -36,19 +40,28 @@ class EpisodeLog:
                                   self.ret.data_ptr(), self.len.data_ptr(), self.env.data_ptr(), self.step.data_ptr(),
                                   self.cap)
 
-    def drain(self):
+    def read_header(self):
+        """(count, sum_ret, sum_len): one 24-byte D2H copy (synchronises the current stream)."""
+        self._hdr_host.copy_(self._hdr, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n = int(self._hdr_host[0:4].view(torch.int32).item())
+        s = self._hdr_host[8:24].view(torch.float64).tolist()
+        return n, s[0], s[1]
+
+    def clear(self):
+        self._hdr.zero_()
+
+    def drain(self, with_entries: bool = True):
         """D2H read + clear.  Returns (count, sum_ret, sum_len, entries sorted by (step, env))."""
-        n = int(self.count.item())
-        sums = self.sums.tolist()
+        n, sum_ret, sum_len = self.read_header()
         k = min(n, self.cap)
         entries = []
-        if k:
+        if k and with_entries:
             st, ev = self.step[:k].tolist(), self.env[:k].tolist()
             rt, ln = self.ret[:k].tolist(), self.len[:k].tolist()
             entries = sorted(zip(st, ev, rt, ln))
-        self.count.zero_()
-        self.sums.zero_()
-        return n, sums[0], sums[1], entries
+        self.clear()
+        return n, sum_ret, sum_len, entries
 
 
 class VecEnv:

@@ -143,7 +143,7 @@ def test_full_update_vs_oracle(env_id, N, T):
         # Adam normalises the step, so tiny gradient differences can move a weight by O(lr * 1e-3)
         np.testing.assert_allclose(tr.agent.flat_params.cpu().numpy(), p, rtol=0, atol=2e-5)
         assert tr.adam_step == k
-    assert abs(tr.explained_variance()) < 10
+    assert np.isfinite(tr.explained_variance())
 
 
 def test_reference_shape_learning_curve():
