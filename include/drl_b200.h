@@ -146,6 +146,10 @@ int drl_clip_adam(const drl_net_t* net, float* params, const float* grad, float*
                   int64_t step, double lr, double beta1, double beta2, double eps, double max_grad_norm,
                   double grad_scale, float* packed_out, float* norm_out, void* stream);
 
+/* ---- diagnostics: runs one tcgen05.mma operand-layout combination of the update kernel on caller matrices
+ * (fp32 row-major in, fp32 row-major out; operands are rounded to bf16).  See csrc/umma_selftest.cu. ---- */
+int drl_selftest_umma(int32_t mode, int32_t variant, const float* a, const float* b, float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
