@@ -156,7 +156,8 @@ def run_b200(args):
                 else f"C3: PPO CartPole-v1, 65,536 envs/GPU x 128 steps env-sharded across {world} B200, NCCL gradient all-reduce"
                 if (envs == 65_536 and T == 128 and args.env_id == "CartPole-v1") else f"custom: {args.env_id}, {envs} envs/GPU x {T} steps")
     total_updates = args.warmup + 2 * args.steps + 8
-    cfg = PPOConfig(env_id=args.env_id, num_envs=envs, num_steps=T, total_timesteps=envs * T * world * total_updates, seed=1)
+    cfg = PPOConfig(env_id=args.env_id, num_envs=envs, num_steps=T, total_timesteps=envs * T * world * total_updates, seed=1,
+                    update_precision=args.precision)
     tr = PPOTrainer(cfg, rank=rank, world=world, device=dev)
     nu = cfg.num_updates(world)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -219,14 +220,17 @@ def run_b200(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"ppo_grad_kernel@{M}")
+            traffic = json.load(open(tpath)).get(f"{'ppo_grad_tc_kernel' if args.precision == 'bf16' else 'ppo_grad_kernel'}@{M}")
         except Exception:
             traffic = None
-    roofline = {"kernel": "ppo_grad_kernel (+grad_reduce_kernel)", "bound": "tensor", "achieved": achieved_tf,
+    tc = args.precision == "bf16"
+    roofline = {"kernel": ("ppo_grad_tc_kernel" if tc else "ppo_grad_kernel") + " (+grad_reduce_kernel)", "bound": "tensor", "achieved": achieved_tf,
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops_sustained"],
                 "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "flops_per_launch": flops_per_launch, "launch_ms": g["mean_ms"],
-                "note": "FP32 CUDA-core (FFMA) path in this round; the tensor-pipe peak is the roof the tcgen05 path will be held to",
+                "note": ("tcgen05 path: the three HxH GEMMs and all weight-gradient reductions run on the tensor pipe (bf16 operands, "
+                         "fp32 TMEM accumulators); FLOPs counted are the algorithmic 3F per sample" if tc else
+                         "FP32 CUDA-core (FFMA) path; the tensor-pipe peak is the roof the tcgen05 path is held to"),
                 "hbm": {"achieved_gbs": GRAD_BYTES_PER_SAMPLE[args.env_id] * M / (g["mean_ms"] * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"]},
                 "end_to_end": {"hbm_frac": value * BYTES_PER_ENV_STEP[args.env_id] / world / 1e9 / peaks["hbm_gbs"],
                                "tensor_frac": value * 13 * F / world / 1e12 / peaks["bf16_tflops_sustained"]},
@@ -249,8 +253,8 @@ def run_b200(args):
     line = {
         "metric": "PPO env-steps/sec (rollout+update) CartPole-v1", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "env_id": args.env_id, "envs_per_gpu": envs, "num_steps": T, "hidden": 64,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tc else "f32", "data": "synthetic",
+        "config": {"workload": workload, "precision": ("update GEMMs bf16 x bf16 -> fp32 on tcgen05; rollout, env, GAE, loss, Adam fp32/fp64" if tc else "fp32"), "env_id": args.env_id, "envs_per_gpu": envs, "num_steps": T, "hidden": 64,
                    "minibatch_size": M, "update_epochs": cfg.update_epochs, "optimizer_steps_per_update": cfg.update_epochs * tr.n_mb,
                    "parallelism": f"env-sharded x{world}", "l2": "flushed between updates (256 MiB memset outside the timed events); "
                    "every update regenerates its own rollout data"},
@@ -276,6 +280,8 @@ def main():
     ap.add_argument("--env-id", default="CartPole-v1")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="update GEMMs: bf16 = tcgen05 tensor cores (bf16 operands, fp32 accumulate), fp32 = CUDA cores")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -70,7 +70,7 @@ int64_t drl_param_count(const drl_net_t* net) {
 }
 int64_t drl_packed_count(const drl_net_t* net) {
     if (check_net(net) != DRL_OK) return -1;
-    return net->obs_dim == 4 ? Packed<4, 2>::ALL : Packed<6, 3>::ALL;
+    return net->obs_dim == 4 ? Packed<4, 2>::TOTAL : Packed<6, 3>::TOTAL;
 }
 int drl_record_width(const drl_net_t* net) {
     if (check_net(net) != DRL_OK) return -1;

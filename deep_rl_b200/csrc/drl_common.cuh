@@ -74,6 +74,19 @@ struct Packed {
     static constexpr int FWD = (FWD_RAW + 3) / 4 * 4;  // 16-byte multiple for the bulk copy
     static constexpr int W2P = FWD;
     static constexpr int ALL = W2P + 2 * H * H;
+    // ---- tensor-core section (update_tc.cu), natural unit order, staged by one TMA bulk copy ----
+    //   TC_W2 : bf16 [2][64 rows o][64 i] as two SW128 UMMA tiles (16 KB)
+    //   TC_W1 : fp32 [2][H][OW] (OW = 4 or 8, zero padded), TC_B1 / TC_B2 : fp32 [2][H]
+    //   TC_W4 : fp32 [A+1][H] (actor rows, then the critic row), TC_B4 : fp32 [4]
+    static constexpr int OW = O <= 4 ? 4 : 8;
+    static constexpr int TC_W2 = ALL;
+    static constexpr int TC_W1 = TC_W2 + 2 * H * H / 2;
+    static constexpr int TC_B1 = TC_W1 + 2 * H * OW;
+    static constexpr int TC_B2 = TC_B1 + 2 * H;
+    static constexpr int TC_W4 = TC_B2 + 2 * H;
+    static constexpr int TC_B4 = TC_W4 + (A + 1) * H;
+    static constexpr int TC_END = TC_B4 + 4;
+    static constexpr int TOTAL = TC_END;
     // canonical (state_dict) layout
     static constexpr int C_NET = H * O + H + H * H + H;          // trunk params per net
     static constexpr int C_ACTOR = C_NET + A * H + A;

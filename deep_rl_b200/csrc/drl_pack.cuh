@@ -1,6 +1,8 @@
 // drl_pack.cuh -- canonical (state_dict order) <-> packed (kernel) parameter index map, and the
 // layout of the caller-owned update workspace.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "drl_common.cuh"
 
 namespace drl {
@@ -17,28 +19,43 @@ __device__ __forceinline__ void packed_store(float* __restrict__ packed, int i, 
     if (r < H * O) {
         const int o = r / O, k = r % O;
         packed[P::W1T + (net * O + k) * H + perm_pos(o)] = v;
+        packed[P::TC_W1 + (net * H + o) * P::OW + k] = v;
         return;
     }
     r -= H * O;
-    if (r < H) { packed[P::B1 + net * H + perm_pos(r)] = v; return; }
+    if (r < H) {
+        packed[P::B1 + net * H + perm_pos(r)] = v;
+        packed[P::TC_B1 + net * H + r] = v;
+        return;
+    }
     r -= H;
     if (r < H * H) {
         const int o = r / H, k = r % H;
         packed[P::W2T + (net * H + k) * H + perm_pos(o)] = v;
         packed[P::W2P + (net * H + o) * H + perm_pos(k)] = v;
+        // bf16 SW128 tile image: row o, 16-byte chunk k/8 stored at chunk position (k/8) ^ (o & 7)
+        unsigned char* tc = reinterpret_cast<unsigned char*>(packed + P::TC_W2);
+        const int off = net * (H * H * 2) + o * 128 + ((((k >> 3) ^ (o & 7)) << 4)) + (k & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(tc + off) = __float2bfloat16_rn(v);
         return;
     }
     r -= H * H;
-    if (r < H) { packed[P::B2 + net * H + perm_pos(r)] = v; return; }
+    if (r < H) {
+        packed[P::B2 + net * H + perm_pos(r)] = v;
+        packed[P::TC_B2 + net * H + r] = v;
+        return;
+    }
     r -= H;
     const int nout = net == 0 ? A : 1;
     if (r < nout * H) {
         const int a = r / H, k = r % H;
         packed[P::W4 + (net * A + a) * H + perm_pos(k)] = v;
+        packed[P::TC_W4 + (net == 0 ? a : A) * H + k] = v;
         return;
     }
     r -= nout * H;
     packed[P::B4 + net * A + r] = v;
+    packed[P::TC_B4 + (net == 0 ? r : A)] = v;
 }
 
 // ---- update workspace (caller-owned, zero-initialised once) ----

@@ -6,6 +6,7 @@
 //   clip_adam_kernel  clip_grad_norm_ + Adam (+ refresh of the packed kernel layout), ppo.py:191-192
 #include "drl_mlp.cuh"
 #include "drl_pack.cuh"
+#include "drl_update.cuh"
 
 namespace drl {
 
@@ -24,18 +25,6 @@ struct GradLocal {                    // lane-local gradient accumulators (units
     float b2[UPL];
     float w4[A][UPL];
     float b4[A];
-};
-
-struct GradArgs {
-    const float* packed;
-    const float* rec;
-    const uint32_t* idx;
-    uint32_t mb_start, mb_count;
-    const float* adv_stats;   // [2] mean, std
-    float clip_coef, ent_coef, vf_coef;
-    float* grad_part;         // [gridDim.x][ppad]
-    float* loss_part;         // [gridDim.x][LOSS_TERMS]
-    int ppad;
 };
 
 template <int O, int A, int OP, int RW>
@@ -476,6 +465,10 @@ int launch_grad(const GradArgs& g, int P, float* grad_out, float* loss_terms_out
     if ((uint32_t)grid > ntiles) grid = (int)ntiles;
     ppo_grad_kernel<O, A, OP, RW><<<grid, GT, smem, st>>>(g);
     DRL_LAUNCH_CHECK("ppo_grad_kernel");
+    return launch_grad_reduce(g, grid, P, grad_out, loss_terms_out, st);
+}
+
+int launch_grad_reduce(const GradArgs& g, int grid, int P, float* grad_out, float* loss_terms_out, cudaStream_t st) {
     grad_reduce_kernel<<<(P + 31) / 32, dim3(32, 8), 0, st>>>(g.grad_part, g.loss_part, grid, g.ppad, P, g.mb_count, g.ent_coef,
                                                        g.vf_coef, grad_out, loss_terms_out);
     DRL_LAUNCH_CHECK("grad_reduce_kernel");
@@ -490,7 +483,7 @@ extern "C" {
 
 int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const float* rec, const uint32_t* idx,
                            uint32_t mb_start, uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef,
-                           float* grad_out, float* loss_terms_out, void* workspace, size_t workspace_bytes, void* stream) {
+                           float* grad_out, float* loss_terms_out, void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
     int rc = check_net(net);
     if (rc != DRL_OK) return rc;
     DRL_REQUIRE(packed && rec && adv_stats && coef && grad_out && workspace, "drl_ppo_minibatch_grad: NULL pointer");
@@ -504,6 +497,7 @@ int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const floa
     g.grad_part = reinterpret_cast<float*>((char*)workspace + w.grad_partials);
     g.loss_part = reinterpret_cast<float*>((char*)workspace + w.loss_partials);
     g.ppad = w.ppad;
+    if (flags & DRL_GRAD_TENSOR_CORES) return launch_grad_tc(net, g, P, grad_out, loss_terms_out, as_stream(stream));
     if (net->obs_dim == 4) return launch_grad<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, as_stream(stream));
     return launch_grad<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, as_stream(stream));
 }

@@ -1,0 +1,435 @@
+// update_tc.cu -- tensor-core (tcgen05 / TMEM) implementation of the PPO minibatch gradient,
+// deep_rl/ppo.py:159-190.  Same inputs, outputs and per-CTA partial-gradient format as ppo_grad_kernel
+// (update_ops.cu); operands of the GEMMs are bf16, accumulation is fp32 in tensor memory.
+//
+// One persistent CTA per SM, 256 threads.  A tile is 128 samples = the 128 TMEM lanes; thread (warp w, lane l)
+// owns sample row r = 32*(w&3)+l of net (w>>2) (0 = actor trunk, 1 = critic trunk).  Per tile:
+//   P0  gather the 32-byte records, layer 1 on CUDA cores (K = 4/6 is degenerate for UMMA), h1 -> bf16 SW128 tile
+//   MMA z2 = h1 . W2^T                       (per net: M128 N64 K64, A/B K-major)
+//   P1  tcgen05.ld z2, tanh, heads, clipped-surrogate / value / entropy loss and their closed-form output
+//       gradients, dz2 = (dout . W4) * (1 - h2^2); h2, dz2, dout -> bf16 tiles
+//   MMA dh1 = dz2 . W2                       (M128 N64 K64, B MN-major: the same W2 tile, transposed by descriptor)
+//       dW2 += dz2^T . h1                    (M128 N128 K128, both operands MN-major: the activation tiles again)
+//       db2 += dz2^T . [obs|1]   dW4 += h2^T . dout      (M128 N16 K128)
+//   P2  tcgen05.ld dh1, dz1 = dh1 * (1 - h1^2) -> bf16 tile
+//   MMA [dW1|db1] += dz1^T . [obs|1]         (M128 N16 K128)   -- overlaps the next tile's P0
+// All weight-gradient accumulators live in TMEM for the whole kernel (304 of 512 columns) and are written once,
+// as this CTA's partial gradient, at the end.
+#include "drl_pack.cuh"
+#include "drl_umma.cuh"
+#include "drl_update.cuh"
+
+namespace drl {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_TILE = 128;
+// TMEM columns
+constexpr uint32_t C_Z = 0, C_W2 = 128, C_B2 = 256, C_W4 = 272, C_W1 = 288, TC_COLS = 512;
+
+template <int O, int A>
+struct TcSmem {
+    using P = Packed<O, A>;
+    static constexpr int W_BYTES = (P::TC_END - P::TC_W2) * 4;   // bf16 W2 tiles (16 KB) + fp32 small weights
+    static constexpr int OFF_W = 0;
+    static constexpr int OFF_H1 = (OFF_W + W_BYTES + 1023) / 1024 * 1024;
+    static constexpr int OFF_H2 = OFF_H1 + 32768;
+    static constexpr int OFF_DZ = OFF_H2 + 32768;
+    static constexpr int OFF_OBS = OFF_DZ + 32768;     // two NS16 buffers (tile parity)
+    static constexpr int OFF_DOUT = OFF_OBS + 8192;    // one NS16 buffer
+    static constexpr int OFF_BAR = OFF_DOUT + 4096;    // 4 mbarriers + TMEM slot
+    static constexpr int OFF_RED = OFF_BAR + 64;
+    static constexpr int TOTAL = OFF_RED + 8 * 12 * 4 + 1024;   // + alignment slack
+};
+
+__device__ __forceinline__ void ld64(uint32_t taddr, float (&v)[64]) {
+    float lo[32], hi[32];
+    umma::ld32(taddr, lo);
+    umma::ld32(taddr + 32, hi);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { v[i] = lo[i]; v[32 + i] = hi[i]; }
+}
+
+template <int O, int A, int OP, int RW>
+__global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) {
+    using P = Packed<O, A>;
+    using S = TcSmem<O, A>;
+    constexpr int OW = P::OW;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* tW2 = sm + S::OFF_W;
+    const float* sW1 = reinterpret_cast<const float*>(sm + S::OFF_W + 2 * H * H * 2);
+    const float* sB1 = sW1 + 2 * H * OW;
+    const float* sB2 = sB1 + 2 * H;
+    const float* sW4 = sB2 + 2 * H;
+    const float* sB4 = sW4 + (A + 1) * H;
+    unsigned char* tH1 = sm + S::OFF_H1;
+    unsigned char* tH2 = sm + S::OFF_H2;
+    unsigned char* tDZ = sm + S::OFF_DZ;
+    unsigned char* tOBS = sm + S::OFF_OBS;
+    unsigned char* tDOUT = sm + S::OFF_DOUT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd, 2 bwd, 3 w1
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 4);
+    float* red = reinterpret_cast<float*>(sm + S::OFF_RED);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int net = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+
+    // ---- prologue: barriers, TMEM, weights by TMA bulk copy ----
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) umma::tmem_alloc(slot, TC_COLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (tid == 0) {
+        mbar_expect_tx(bars, (uint32_t)S::W_BYTES);
+        const char* src = reinterpret_cast<const char*>(g.packed + P::TC_W2);
+        for (uint32_t off = 0; off < (uint32_t)S::W_BYTES; off += 16384u) {
+            const uint32_t n = (uint32_t)S::W_BYTES - off < 16384u ? (uint32_t)S::W_BYTES - off : 16384u;
+            bulk_g2s(sm + S::OFF_W + off, src + off, n, bars);
+        }
+    }
+    const uint32_t tmem = *slot;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this thread's TMEM lane
+    const float adv_mean = g.adv_stats[0], adv_std = g.adv_stats[1];
+    const float inv_m = 1.0f / (float)g.mb_count;
+    mbar_wait(bars, 0);
+
+    const uint32_t aW2 = smem_u32(tW2), aH1 = smem_u32(tH1), aH2 = smem_u32(tH2), aDZ = smem_u32(tDZ);
+    const uint32_t aOBS = smem_u32(tOBS), aDOUT = smem_u32(tDOUT);
+    constexpr uint32_t ID_FWD = umma::make_idesc(128, 64, false, false);
+    constexpr uint32_t ID_DH1 = umma::make_idesc(128, 64, false, true);
+    constexpr uint32_t ID_W2 = umma::make_idesc(128, 128, true, true);
+    constexpr uint32_t ID_N16 = umma::make_idesc(128, 16, true, true);
+
+    float lsum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // pg, v, entropy, kl, clipfrac partial sums
+    float gb4[4] = {0.f, 0.f, 0.f, 0.f};         // head-bias gradients: actor slots 0..A-1, critic slot 3
+
+    const uint32_t ntiles = (g.mb_count + TC_TILE - 1) / TC_TILE;
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t par = it & 1u;
+        unsigned char* tOBSb = tOBS + par * 4096;
+
+        // ================= P0: gather + layer 1 =================
+        float x[OW];
+#pragma unroll
+        for (int i = 0; i < OW; ++i) x[i] = 0.0f;
+        float logp_old = 0.f, adv = 0.f, val_old = 0.f;
+        int act = 0;
+        const uint32_t pos = tile * TC_TILE + (uint32_t)r;
+        const bool valid = pos < g.mb_count;
+        if (valid) {
+            const uint32_t i = g.mb_start + pos;
+            const size_t s = g.idx ? g.idx[i] : i;
+            const float4* r4 = reinterpret_cast<const float4*>(g.rec + s * RW);
+#pragma unroll
+            for (int q = 0; q < OP / 4; ++q) {
+                const float4 v4 = __ldg(r4 + q);
+                x[4 * q] = v4.x; x[4 * q + 1] = v4.y; x[4 * q + 2] = v4.z; x[4 * q + 3] = v4.w;
+            }
+            const float4 t4 = __ldg(r4 + RW / 4 - 1);
+            logp_old = t4.x; adv = t4.y; val_old = t4.z; act = __float_as_int(t4.w);
+        }
+        {
+            float h[64];
+            const float* w1 = sW1 + net * H * OW;
+            const float* b1 = sB1 + net * H;
+#pragma unroll
+            for (int k4 = 0; k4 < 16; ++k4) {
+                const float4 bb = *reinterpret_cast<const float4*>(b1 + 4 * k4);
+                const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 4 * k4 + j;
+                    float z = bv[j];
+#pragma unroll
+                    for (int q = 0; q < OW / 4; ++q) {
+                        const float4 w = *reinterpret_cast<const float4*>(w1 + k * OW + 4 * q);
+                        z = fmaf(x[4 * q + 3], w.w, fmaf(x[4 * q + 2], w.z, fmaf(x[4 * q + 1], w.y, fmaf(x[4 * q], w.x, z))));
+                    }
+                    h[k] = tanh_fast(z);
+                }
+            }
+            umma::store_row_sw128(tH1 + net * 16384, r, h);
+        }
+        if (net == 0) {   // [obs | 1 | 0...] row of the NS16 tile (B operand of the dW1/db1 and db2 GEMMs)
+            float o16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o16[i] = i < O ? x[i] : (i == O ? 1.0f : 0.0f);
+            umma::store_row_ns16(tOBSb, TC_TILE, r, o16);
+        }
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+                    umma::mma(tmem + C_Z + n2 * 64, umma::make_desc(aH1 + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
+                              umma::make_desc(aW2 + n2 * 8192 + kb * 32, 16, 1024, umma::LAYOUT_SW128), ID_FWD, kb > 0);
+            umma::commit(bars + 1);
+        }
+        mbar_wait(bars + 1, par);
+        umma::fence_after_sync();
+
+        // ================= P1: heads, loss, output gradients, dz2 =================
+        {
+            float h[64];
+            ld64(trow + C_Z + net * 64, h);
+            const float* b2 = sB2 + net * H;
+#pragma unroll
+            for (int k4 = 0; k4 < 16; ++k4) {
+                const float4 bb = *reinterpret_cast<const float4*>(b2 + 4 * k4);
+                h[4 * k4 + 0] = tanh_fast(h[4 * k4 + 0] + bb.x);
+                h[4 * k4 + 1] = tanh_fast(h[4 * k4 + 1] + bb.y);
+                h[4 * k4 + 2] = tanh_fast(h[4 * k4 + 2] + bb.z);
+                h[4 * k4 + 3] = tanh_fast(h[4 * k4 + 3] + bb.w);
+            }
+            umma::store_row_sw128(tH2 + net * 16384, r, h);
+
+            constexpr int NO = A;                  // head outputs handled by an actor thread; critic uses slot 0
+            float out[NO];
+            const int wrow0 = net == 0 ? 0 : A;    // first head row of this net in sW4 / sB4
+#pragma unroll
+            for (int a = 0; a < NO; ++a) out[a] = 0.0f;
+#pragma unroll
+            for (int a = 0; a < NO; ++a) {
+                if (net == 0 || a == 0) {
+                    const float* w = sW4 + (wrow0 + a) * H;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int k4 = 0; k4 < 16; ++k4) {
+                        const float4 ww = *reinterpret_cast<const float4*>(w + 4 * k4);
+                        s0 = fmaf(h[4 * k4 + 0], ww.x, s0);
+                        s1 = fmaf(h[4 * k4 + 1], ww.y, s1);
+                        s2 = fmaf(h[4 * k4 + 2], ww.z, s2);
+                        s3 = fmaf(h[4 * k4 + 3], ww.w, s3);
+                    }
+                    out[a] = (s0 + s1) + (s2 + s3) + sB4[wrow0 + a];
+                }
+            }
+            float d[NO];
+#pragma unroll
+            for (int a = 0; a < NO; ++a) d[a] = 0.0f;
+            if (valid) {
+                if (net == 0) {
+                    float m = out[0];
+#pragma unroll
+                    for (int a = 1; a < A; ++a) m = fmaxf(m, out[a]);
+                    float se = 0.f;
+#pragma unroll
+                    for (int a = 0; a < A; ++a) se += expf(out[a] - m);
+                    const float lse = m + logf(se);
+                    float lp[A], p[A];
+                    float ent = 0.f, new_logp = 0.f;
+#pragma unroll
+                    for (int a = 0; a < A; ++a) {
+                        lp[a] = out[a] - lse;
+                        p[a] = expf(lp[a]);
+                        ent -= p[a] * lp[a];
+                        if (a == act) new_logp = lp[a];
+                    }
+                    const float nadv = (adv - adv_mean) / (adv_std + 1e-8f);
+                    const float logratio = new_logp - logp_old;
+                    const float ratio = expf(logratio);
+                    const float pg1 = -nadv * ratio;
+                    const float pg2 = -nadv * fminf(fmaxf(ratio, 1.0f - g.clip_coef), 1.0f + g.clip_coef);
+                    const float dpg = pg1 >= pg2 ? pg1 : 0.0f;
+                    lsum[0] += fmaxf(pg1, pg2);
+                    lsum[2] += ent;
+                    lsum[3] += (ratio - 1.0f) - logratio;
+                    lsum[4] += fabsf(ratio - 1.0f) > g.clip_coef ? 1.0f : 0.0f;
+#pragma unroll
+                    for (int a = 0; a < A; ++a) {
+                        const float onehot = a == act ? 1.0f : 0.0f;
+                        d[a] = inv_m * (dpg * (onehot - p[a]) + g.ent_coef * p[a] * (lp[a] + ent));
+                        gb4[a] += d[a];
+                    }
+                } else {
+                    const float v = out[0];
+                    const float ret = adv + val_old;
+                    const float vd = v - ret;
+                    const float vu = vd * vd;
+                    const float vdiff = v - val_old;
+                    const float vc = val_old + fminf(fmaxf(vdiff, -g.clip_coef), g.clip_coef);
+                    const float vcd = vc - ret;
+                    const float vcl = vcd * vcd;
+                    lsum[1] += fmaxf(vu, vcl);
+                    const float gcl = (vdiff >= -g.clip_coef && vdiff <= g.clip_coef) ? vcd : 0.0f;
+                    const float gv = vu > vcl ? vd : (vcl > vu ? gcl : 0.5f * (vd + gcl));
+                    d[0] = g.vf_coef * gv * inv_m;
+                    gb4[3] += d[0];
+                }
+            }
+            {   // dout row: actor -> columns 0..A-1 (chunk 0), critic -> column 8 (chunk 1)
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (net == 0) {
+                    q.x = umma::pack_bf16(d[0], d[1]);
+                    if constexpr (A > 2) q.y = umma::pack_bf16(d[2], 0.0f);
+                } else {
+                    q.x = umma::pack_bf16(d[0], 0.0f);
+                }
+                *reinterpret_cast<uint4*>(tDOUT + (size_t)net * TC_TILE * 16 + (size_t)r * 16) = q;
+            }
+            // dz2 = (dout . W4) * (1 - h2^2), in place
+#pragma unroll
+            for (int k4 = 0; k4 < 16; ++k4) {
+                float dh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int a = 0; a < NO; ++a) {
+                    if (net == 0 || a == 0) {
+                        const float4 ww = *reinterpret_cast<const float4*>(sW4 + (wrow0 + a) * H + 4 * k4);
+                        dh[0] = fmaf(d[a], ww.x, dh[0]); dh[1] = fmaf(d[a], ww.y, dh[1]);
+                        dh[2] = fmaf(d[a], ww.z, dh[2]); dh[3] = fmaf(d[a], ww.w, dh[3]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[4 * k4 + j] = dh[j] * fmaf(-h[4 * k4 + j], h[4 * k4 + j], 1.0f);
+            }
+            if (it > 0) mbar_wait(bars + 3, (it - 1) & 1u);   // previous tile's dW1 GEMM has finished reading tDZ
+            umma::store_row_sw128(tDZ + net * 16384, r, h);
+        }
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            const uint32_t acc = it > 0 ? 1u : 0u;
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+                    umma::mma(tmem + C_Z + n2 * 64, umma::make_desc(aDZ + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
+                              umma::make_desc(aW2 + n2 * 8192 + kb * 2048, 8192, 1024, umma::LAYOUT_SW128), ID_DH1, kb > 0);
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb)
+                umma::mma(tmem + C_W2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                          umma::make_desc(aH1 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128), ID_W2, acc | (kb > 0));
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb)
+                umma::mma(tmem + C_B2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                          umma::make_desc(aOBS + par * 4096 + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb)
+                umma::mma(tmem + C_W4, umma::make_desc(aH2 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                          umma::make_desc(aDOUT + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
+            umma::commit(bars + 2);
+        }
+        mbar_wait(bars + 2, par);
+        umma::fence_after_sync();
+
+        // ================= P2: dz1 = dh1 * (1 - h1^2) =================
+        {
+            float dh[64];
+            ld64(trow + C_Z + net * 64, dh);
+            const unsigned char* h1row = tH1 + net * 16384;
+            unsigned char* dzrow = tDZ + net * 16384;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {   // 16-byte chunk at a time: h1 (bf16) in, dz1 (bf16) out
+                const uint32_t off = umma::sw128_off(r, c);
+                const uint4 q = *reinterpret_cast<const uint4*>(h1row + off);
+                const float hv[8] = {umma::bf16_lo(q.x), umma::bf16_hi(q.x), umma::bf16_lo(q.y), umma::bf16_hi(q.y),
+                                     umma::bf16_lo(q.z), umma::bf16_hi(q.z), umma::bf16_lo(q.w), umma::bf16_hi(q.w)};
+                float z[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) z[j] = dh[8 * c + j] * fmaf(-hv[j], hv[j], 1.0f);
+                uint4 o4;
+                o4.x = umma::pack_bf16(z[0], z[1]); o4.y = umma::pack_bf16(z[2], z[3]);
+                o4.z = umma::pack_bf16(z[4], z[5]); o4.w = umma::pack_bf16(z[6], z[7]);
+                *reinterpret_cast<uint4*>(dzrow + off) = o4;
+            }
+        }
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            const uint32_t acc = it > 0 ? 1u : 0u;
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb)
+                umma::mma(tmem + C_W1, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                          umma::make_desc(aOBS + par * 4096 + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
+            umma::commit(bars + 3);
+        }
+    }
+    if (it > 0) mbar_wait(bars + 3, (it - 1) & 1u);
+    umma::fence_after_sync();
+
+    // ================= epilogue: this CTA's partial gradient, canonical layout =================
+    float* part = g.grad_part + (size_t)blockIdx.x * g.ppad;
+    if (warp < 4) {
+        const int no = r >> 6, o = r & 63;             // TMEM lane r = hidden unit o of net `no`
+        const int base = no * P::C_ACTOR;
+        float v16[16];
+        umma::ld16(trow + C_B2, v16);
+        part[base + H * O + H + H * H + o] = v16[O];   // db2
+        umma::ld16(trow + C_W1, v16);
+#pragma unroll
+        for (int i = 0; i < O; ++i) part[base + o * O + i] = v16[i];   // dW1
+        part[base + H * O + o] = v16[O];                               // db1
+        umma::ld16(trow + C_W4, v16);
+        if (no == 0) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) part[P::C_NET + a * H + o] = v16[a];   // actor head
+        } else {
+            part[P::C_ACTOR + P::C_NET + o] = v16[8];                           // critic head
+        }
+    }
+    {   // dW2: the diagonal 64x64 blocks of the 128x128 accumulator
+        const int no = r >> 6, o = r & 63;
+        if (no == net) {   // warp-uniform
+            float v[64];
+            ld64(trow + C_W2 + net * 64, v);
+            float* dst = part + net * P::C_ACTOR + H * O + H + o * H;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) dst[i] = v[i];
+        }
+    }
+    // loss partial sums and head-bias gradients: fold the 256 threads
+    {
+        float vals[9] = {lsum[0], lsum[1], lsum[2], lsum[3], lsum[4], gb4[0], gb4[1], gb4[2], gb4[3]};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float s = warp_sum(vals[k]);
+            if (lane == 0) red[warp * 12 + k] = s;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 9) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w * 12 + tid];
+        if (tid < 5) g.loss_part[blockIdx.x * LOSS_TERMS + tid] = s;
+        else if (tid - 5 < A) part[P::C_NET + A * H + (tid - 5)] = s;              // actor head bias
+        else if (tid == 8) part[P::C_ACTOR + P::C_NET + H] = s;                    // critic head bias
+    }
+    if (warp == 1) umma::tmem_dealloc(tmem, TC_COLS);
+}
+
+template <int O, int A, int OP, int RW>
+static int launch_tc(const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st) {
+    const int smem = TcSmem<O, A>::TOTAL;
+    DRL_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<O, A, OP, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const uint32_t ntiles = (g.mb_count + TC_TILE - 1) / TC_TILE;
+    int grid = sm_count();
+    if (grid > MAX_GRAD_CTAS) grid = MAX_GRAD_CTAS;
+    if ((uint32_t)grid > ntiles) grid = (int)ntiles;
+    ppo_grad_tc_kernel<O, A, OP, RW><<<grid, TC_THREADS, smem, st>>>(g);
+    DRL_LAUNCH_CHECK("ppo_grad_tc_kernel");
+    return launch_grad_reduce(g, grid, P, grad_out, loss_terms_out, st);
+}
+
+int launch_grad_tc(const drl_net_t* net, const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st) {
+    if (net->obs_dim == 4) return launch_tc<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, st);
+    return launch_tc<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, st);
+}
+
+}  // namespace drl

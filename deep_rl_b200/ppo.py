@@ -49,6 +49,7 @@ class PPOConfig:
     hidden: int = 64
     num_minibatches: int = 4     # reference: minibatch_size = num_steps // 4
     anneal_lr: bool = True
+    update_precision: str = "bf16"   # "bf16": tcgen05 tensor-core update (bf16 operands, fp32 accumulate); "fp32": CUDA-core update
 
     @property
     def batch_size(self) -> int:             # samples per rank per update
@@ -130,6 +131,9 @@ class PPOTrainer:
         self.ws_bytes = int(self.L.drl_workspace_bytes(C.byref(self.net)))
         self.workspace = torch.zeros(self.ws_bytes, dtype=u8, device=dev)
         self.coef = _lib.PpoCoefT(cfg.clip_coef, cfg.ent_coef, cfg.vf_coef)
+        if cfg.update_precision not in ("bf16", "fp32"):
+            raise ValueError(f"update_precision={cfg.update_precision!r}")
+        self.grad_flags = 1 if cfg.update_precision == "bf16" else 0
         self.adam_step = 0
         self.update_idx = 0
         self.global_step = 0       # env steps taken on this rank's envs x world (reference counter at N=1)
@@ -194,7 +198,7 @@ class PPOTrainer:
                     _lib.check(self.L.drl_ppo_minibatch_grad(
                         net, self.agent.packed.data_ptr(), self.records.data_ptr(), self.idx.data_ptr(), start, count,
                         self.adv_stats.data_ptr() + 8 * k, C.byref(self.coef), self.grad.data_ptr(),
-                        self.loss_terms.data_ptr() + 32 * row, self.workspace.data_ptr(), self.ws_bytes, st))
+                        self.loss_terms.data_ptr() + 32 * row, self.workspace.data_ptr(), self.ws_bytes, self.grad_flags, st))
                 if self.world > 1:
                     with _Phase(self, "allreduce"):
                         _dist.all_reduce_sum(self.grad)       # the only collective: NCCL over NVLink

@@ -134,10 +134,11 @@ int drl_adv_stats(const drl_net_t* net, const float* rec, const uint32_t* idx, u
 /* ---- loss + backward of one minibatch, ppo.py:159-187 + backward of ppo.py:190 ----
  * grad_out [P] canonical layout, mean over the mb_count samples; loss_terms_out[8] =
  * {loss, pg_loss, v_loss, entropy, approx_kl, clipfrac, 0, 0}. */
+#define DRL_GRAD_TENSOR_CORES 1u   /* flags: tcgen05 path (bf16 operands, fp32 accumulate) instead of FP32 CUDA cores */
 int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const float* rec, const uint32_t* idx,
                            uint32_t mb_start, uint32_t mb_count, const float* adv_stats /*[2] mean,std*/,
                            const drl_ppo_coef_t* coef, float* grad_out, float* loss_terms_out,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
 /* ---- clip_grad_norm_ + Adam, ppo.py:191-192 (after the gradient all-reduce) ----
  * grad is multiplied by grad_scale (1/world) first; `step` is the 1-based Adam step of this call.

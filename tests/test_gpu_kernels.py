@@ -281,7 +281,7 @@ def _make_records(obs, act, logp, adv, val, O, RW):
     return rec
 
 
-def _grad_gpu(params, rec, idx, start, count, O, A, coef=(0.2, 0.01, 0.5), stats=None):
+def _grad_gpu(params, rec, idx, start, count, O, A, coef=(0.2, 0.01, 0.5), stats=None, flags=0):
     L = _lib()
     d = _dev()
     net, p, packed = _pack(params, O, A)
@@ -303,7 +303,7 @@ def _grad_gpu(params, rec, idx, start, count, O, A, coef=(0.2, 0.01, 0.5), stats
     terms = torch.zeros(8, dtype=torch.float32, device=d)
     cf = L.PpoCoefT(*coef)
     L.check(L.lib().drl_ppo_minibatch_grad(C.byref(net), packed.data_ptr(), t_rec.data_ptr(), L.ptr(t_idx), start, count, st_ptr,
-                                           C.byref(cf), grad.data_ptr(), terms.data_ptr(), ws.data_ptr(), ws_bytes, L.stream_ptr()))
+                                           C.byref(cf), grad.data_ptr(), terms.data_ptr(), ws.data_ptr(), ws_bytes, flags, L.stream_ptr()))
     return grad.cpu().numpy(), terms.cpu().numpy(), st.cpu().numpy()
 
 
@@ -345,6 +345,72 @@ def test_minibatch_grad_vs_torch_oracle(O, A, B, M):
         np.testing.assert_allclose(terms[:4], wt, rtol=2e-5, atol=2e-6)
         np.testing.assert_allclose(grad, wg, rtol=2e-4, atol=2e-6)
         assert 0.05 < terms[5] < 0.95      # clip fraction: both branches exercised
+
+
+def _rel_l2(a, b):
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def test_tc_minibatch_grad_vs_reference_golden(golden):
+    """tcgen05 path (bf16 operands, fp32 accumulation) against the reference's own gradients: bf16 tolerance."""
+    g = golden
+    rec = _make_records(g["u0_observations"][:128], g["u0_actions"][:128], g["u0_log_probs"][:128],
+                        g["u0_advantages"][:128], g["u0_values"][:128], 4, 8)
+    params = g["init_params"]
+    for i in range(16):
+        perm = g["perms"][i // 4]
+        grad, terms, _ = _grad_gpu(params, rec, perm, (i % 4) * 32, 32, 4, 2, flags=1)
+        np.testing.assert_allclose(terms[:4], g["mb_terms"][i], rtol=2e-2, atol=5e-3, err_msg=f"minibatch {i}")
+        assert _rel_l2(grad, g["mb_grad_pre"][i]) < 3e-2, (i, _rel_l2(grad, g["mb_grad_pre"][i]))
+        params = g["mb_params_after"][i]
+
+
+@pytest.mark.parametrize("O,A,B,M", [(4, 2, 4096, 1024), (6, 3, 3000, 750), (4, 2, 100_000, 25_000), (4, 2, 70, 70), (4, 2, 129, 129)])
+def test_tc_minibatch_grad_vs_torch_oracle(O, A, B, M):
+    rng = np.random.default_rng(B)
+    RW = 8 if O <= 4 else 16
+    params = _rand_params(O, A, seed=5)
+    obs = rng.normal(size=(B, O)).astype(np.float32)
+    act = rng.integers(0, A, size=B)
+    logits, v = po.mlp_forward(torch.tensor(params), torch.tensor(obs), O, 64, A)
+    logp_all = torch.log_softmax(logits, -1).numpy()
+    logp_old = (logp_all[np.arange(B), act] + rng.normal(scale=0.15, size=B)).astype(np.float32)
+    val_old = (v.numpy() + rng.normal(scale=0.3, size=B)).astype(np.float32)
+    adv = rng.normal(size=B).astype(np.float32) * 2 + 0.3
+    ret = adv + val_old
+    rec = _make_records(obs, act, logp_old, adv, val_old, O, RW)
+    idx = clib.permutation(B, 3, 1, 0)
+    for k in range(min(2, B // M)):
+        sel = idx[k * M:(k + 1) * M].astype(np.int64)
+        grad, terms, st = _grad_gpu(params, rec, idx, k * M, M, O, A, flags=1)
+        wt, wg = po.minibatch_loss_and_grad(params, obs[sel], act[sel], logp_old[sel], adv[sel], ret[sel], val_old[sel], O, 64, A)
+        g32, t32, _ = _grad_gpu(params, rec, idx, k * M, M, O, A, flags=0)
+        print(f"O={O} B={B} mb={k}: rel L2 grad err tc {_rel_l2(grad, wg):.2e} (fp32 path {_rel_l2(g32, wg):.2e}); terms tc {terms[:4]} want {wt}")
+        np.testing.assert_allclose(terms[:4], wt, rtol=2e-2, atol=5e-3)
+        assert _rel_l2(grad, wg) < 3e-2
+        # every parameter tensor individually (a wrong block would hide in the global norm)
+        off = 0
+        for name, shp in zip(po.PARAM_NAMES, po.param_shapes(O, 64, A)):
+            n = int(np.prod(shp))
+            e = _rel_l2(grad[off:off + n], wg[off:off + n])
+            assert e < 6e-2, (name, e)
+            off += n
+        assert abs(terms[5] - t32[5]) < 0.02       # clip fraction agrees with the fp32 path
+
+
+def test_tc_minibatch_grad_deterministic_and_linear():
+    O, A, B = 4, 2, 131_072
+    rng = np.random.default_rng(1)
+    params = _rand_params(O, A, seed=9)
+    rec = _make_records(rng.normal(size=(B, O)).astype(np.float32), rng.integers(0, A, size=B),
+                        -rng.uniform(0.3, 1.2, size=B).astype(np.float32), rng.normal(size=B).astype(np.float32),
+                        rng.normal(size=B).astype(np.float32), O, 8)
+    g1, t1, _ = _grad_gpu(params, rec, None, 0, B, O, A, stats=[0.0, 1.0], flags=1)
+    g2, t2, _ = _grad_gpu(params, rec, None, 0, B, O, A, stats=[0.0, 1.0], flags=1)
+    assert np.array_equal(g1, g2) and np.array_equal(t1, t2)
+    g32, t32, _ = _grad_gpu(params, rec, None, 0, B, O, A, stats=[0.0, 1.0], flags=0)
+    assert _rel_l2(g1, g32) < 3e-2
+    np.testing.assert_allclose(t1[:4], t32[:4], rtol=2e-2, atol=5e-3)
 
 
 def test_minibatch_grad_linearity_in_coefficients():

@@ -115,7 +115,7 @@ def test_full_update_vs_oracle(env_id, N, T):
     """rollout (GPU) -> [GAE, permutation, statistics, 16 x (loss+backward, clip, Adam)] on GPU vs the CPU oracle
     fed the same rollout buffers."""
     import deep_rl_b200 as drl
-    cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=2, total_timesteps=N * T * 10)
+    cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=2, total_timesteps=N * T * 10, update_precision="fp32")
     tr = drl.PPOTrainer(cfg)
     nu = cfg.num_updates()
     for upd in range(2):
@@ -144,6 +144,24 @@ def test_full_update_vs_oracle(env_id, N, T):
         np.testing.assert_allclose(tr.agent.flat_params.cpu().numpy(), p, rtol=0, atol=2e-5)
         assert tr.adam_step == k
     assert np.isfinite(tr.explained_variance())
+
+
+@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 64, 32), ("Acrobot-v1", 24, 64)])
+def test_full_update_tensor_core_path_tracks_fp32_path(env_id, N, T):
+    """Same seeds, one update: the tcgen05 (bf16) update must stay within bf16 tolerance of the fp32 update."""
+    import deep_rl_b200 as drl
+    out = {}
+    for prec in ("fp32", "bf16"):
+        cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=2, total_timesteps=N * T * 10, update_precision=prec)
+        tr = drl.PPOTrainer(cfg)
+        p0 = tr.agent.flat_params.cpu().numpy().copy()
+        tr.update()
+        torch.cuda.synchronize()
+        out[prec] = (tr.loss_terms.cpu().numpy().copy(), tr.agent.flat_params.cpu().numpy() - p0)
+    np.testing.assert_allclose(out["bf16"][0][:, :4], out["fp32"][0][:, :4], rtol=3e-2, atol=1e-2)
+    d32, d16 = out["fp32"][1], out["bf16"][1]
+    assert np.linalg.norm(d16 - d32) / np.linalg.norm(d32) < 0.15      # 16 Adam-normalised steps
+    assert np.isfinite(d16).all()
 
 
 def test_reference_shape_learning_curve():
