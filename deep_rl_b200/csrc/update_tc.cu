@@ -3,18 +3,22 @@
 // (update_ops.cu); operands of the GEMMs are bf16, accumulation is fp32 in tensor memory.
 //
 // One persistent CTA per SM, 256 threads.  A tile is 128 samples = the 128 TMEM lanes; thread (warp w, lane l)
-// owns sample row r = 32*(w&3)+l of net (w>>2) (0 = actor trunk, 1 = critic trunk).  Per tile:
-//   P0  gather the 32-byte records, layer 1 on CUDA cores (K = 4/6 is degenerate for UMMA), h1 -> bf16 SW128 tile
-//   MMA z2 = h1 . W2^T                       (per net: M128 N64 K64, A/B K-major)
-//   P1  tcgen05.ld z2, tanh, heads, clipped-surrogate / value / entropy loss and their closed-form output
-//       gradients, dz2 = (dout . W4) * (1 - h2^2); h2, dz2, dout -> bf16 tiles
-//   MMA dh1 = dz2 . W2                       (M128 N64 K64, B MN-major: the same W2 tile, transposed by descriptor)
-//       dW2 += dz2^T . h1                    (M128 N128 K128, both operands MN-major: the activation tiles again)
-//       db2 += dz2^T . [obs|1]   dW4 += h2^T . dout      (M128 N16 K128)
-//   P2  tcgen05.ld dh1, dz1 = dh1 * (1 - h1^2) -> bf16 tile
-//   MMA [dW1|db1] += dz1^T . [obs|1]         (M128 N16 K128)   -- overlaps the next tile's P0
-// All weight-gradient accumulators live in TMEM for the whole kernel (304 of 512 columns) and are written once,
-// as this CTA's partial gradient, at the end.
+// owns sample row r = 32*(w&3)+l of net (w>>2) (0 = actor trunk, 1 = critic trunk).  Work per tile k:
+//   P0(k)  layer 1 on CUDA cores from the prefetched 32-byte record (K = 4/6 is degenerate for UMMA),
+//          h1 -> bf16 SW128 tile, [obs|1] -> NS16 tile
+//   MMA    fwd(k):  z2 = h1 . W2^T                      (per net M128 N64 K64, A/B K-major)
+//   P1(k)  tcgen05.ld z2, tanh, heads, clipped-surrogate / value / entropy loss and their closed-form output
+//          gradients, dz2 = (dout . W4) * (1 - h2^2); h2, dz2, dout -> bf16 tiles
+//   MMA    bwd(k):  dh1 = dz2 . W2                      (M128 N64 K64, B MN-major: the same W2 tile, transposed by descriptor)
+//                   dW2 += dz2^T . h1                   (M128 N128 K128, both operands MN-major: the activation tiles again)
+//                   db2 += dz2^T . [obs|1]   dW4 += h2^T . dout          (M128 N16 K128)
+//   P2(k)  tcgen05.ld dh1, dz1 = dh1 * (1 - h1^2) -> bf16 tile
+//   MMA    w1(k):   [dW1|db1] += dz1^T . [obs|1]        (M128 N16 K128)
+// The loop is software-pipelined so that no thread ever waits for a GEMM it has just issued:
+//   X(k): wait fwd(k), P1(k), issue bwd(k)   Y(k): P0(k+1), issue fwd(k+1)   Z(k): wait bwd(k), P2(k), issue w1(k)
+// (h1 and [obs|1] tiles are double-buffered, z2 and dh1 have separate TMEM columns, records are prefetched one
+// tile ahead).  All weight-gradient accumulators live in TMEM for the whole kernel (432 of 512 columns used) and
+// are written once, as this CTA's partial gradient, at the end.
 #include "drl_pack.cuh"
 #include "drl_umma.cuh"
 #include "drl_update.cuh"
@@ -24,15 +28,15 @@ namespace drl {
 constexpr int TC_THREADS = 256;
 constexpr int TC_TILE = 128;
 // TMEM columns
-constexpr uint32_t C_Z = 0, C_W2 = 128, C_B2 = 256, C_W4 = 272, C_W1 = 288, TC_COLS = 512;
+constexpr uint32_t C_ZF = 0, C_DH = 128, C_W2 = 256, C_B2 = 384, C_W4 = 400, C_W1 = 416, TC_COLS = 512;
 
 template <int O, int A>
 struct TcSmem {
     using P = Packed<O, A>;
     static constexpr int W_BYTES = (P::TC_END - P::TC_W2) * 4;   // bf16 W2 tiles (16 KB) + fp32 small weights
     static constexpr int OFF_W = 0;
-    static constexpr int OFF_H1 = (OFF_W + W_BYTES + 1023) / 1024 * 1024;
-    static constexpr int OFF_H2 = OFF_H1 + 32768;
+    static constexpr int OFF_H1 = (OFF_W + W_BYTES + 1023) / 1024 * 1024;   // two buffers x (actor, critic) x 16 KB
+    static constexpr int OFF_H2 = OFF_H1 + 65536;
     static constexpr int OFF_DZ = OFF_H2 + 32768;
     static constexpr int OFF_OBS = OFF_DZ + 32768;     // two NS16 buffers (tile parity)
     static constexpr int OFF_DOUT = OFF_OBS + 8192;    // one NS16 buffer
@@ -47,6 +51,42 @@ __device__ __forceinline__ void ld64(uint32_t taddr, float (&v)[64]) {
     umma::ld32(taddr + 32, hi);
 #pragma unroll
     for (int i = 0; i < 32; ++i) { v[i] = lo[i]; v[32 + i] = hi[i]; }
+}
+
+// tanh on the SFU (one MUFU op, |abs err| ~ 5e-4): below the bf16 rounding the activations get anyway
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int OW>
+struct TcRecord {       // one sample record, held in registers between its prefetch and its use
+    float x[OW];
+    float logp_old, adv, val_old;
+    int act;
+    bool valid;
+};
+
+template <int OW, int OP, int RW>
+__device__ __forceinline__ void tc_load_record(TcRecord<OW>& rc, const GradArgs& g, uint32_t tile, uint32_t ntiles, int r) {
+#pragma unroll
+    for (int i = 0; i < OW; ++i) rc.x[i] = 0.0f;
+    rc.logp_old = 0.f; rc.adv = 0.f; rc.val_old = 0.f; rc.act = 0;
+    const uint32_t pos = tile * TC_TILE + (uint32_t)r;
+    rc.valid = tile < ntiles && pos < g.mb_count;
+    if (rc.valid) {
+        const uint32_t i = g.mb_start + pos;
+        const size_t s = g.idx ? g.idx[i] : i;
+        const float4* r4 = reinterpret_cast<const float4*>(g.rec + s * RW);
+#pragma unroll
+        for (int q = 0; q < OP / 4; ++q) {
+            const float4 v4 = __ldg(r4 + q);
+            rc.x[4 * q] = v4.x; rc.x[4 * q + 1] = v4.y; rc.x[4 * q + 2] = v4.z; rc.x[4 * q + 3] = v4.w;
+        }
+        const float4 t4 = __ldg(r4 + RW / 4 - 1);
+        rc.logp_old = t4.x; rc.adv = t4.y; rc.val_old = t4.z; rc.act = __float_as_int(t4.w);
+    }
 }
 
 template <int O, int A, int OP, int RW>
@@ -74,8 +114,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int net = warp >> 2;
     const int r = (warp & 3) * 32 + lane;
+    const uint32_t ntiles = (g.mb_count + TC_TILE - 1) / TC_TILE;
+    const uint32_t nmy = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles of this CTA (>= 1)
 
-    // ---- prologue: barriers, TMEM, weights by TMA bulk copy ----
+    // ---- prologue: first record in flight, barriers, TMEM, weights by TMA bulk copy ----
+    TcRecord<OW> rec_next;
+    tc_load_record<OW, OP, RW>(rec_next, g, blockIdx.x, ntiles, r);
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
@@ -109,32 +153,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     float lsum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // pg, v, entropy, kl, clipfrac partial sums
     float gb4[4] = {0.f, 0.f, 0.f, 0.f};         // head-bias gradients: actor slots 0..A-1, critic slot 3
 
-    const uint32_t ntiles = (g.mb_count + TC_TILE - 1) / TC_TILE;
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const uint32_t par = it & 1u;
-        unsigned char* tOBSb = tOBS + par * 4096;
-
-        // ================= P0: gather + layer 1 =================
-        float x[OW];
-#pragma unroll
-        for (int i = 0; i < OW; ++i) x[i] = 0.0f;
-        float logp_old = 0.f, adv = 0.f, val_old = 0.f;
-        int act = 0;
-        const uint32_t pos = tile * TC_TILE + (uint32_t)r;
-        const bool valid = pos < g.mb_count;
-        if (valid) {
-            const uint32_t i = g.mb_start + pos;
-            const size_t s = g.idx ? g.idx[i] : i;
-            const float4* r4 = reinterpret_cast<const float4*>(g.rec + s * RW);
-#pragma unroll
-            for (int q = 0; q < OP / 4; ++q) {
-                const float4 v4 = __ldg(r4 + q);
-                x[4 * q] = v4.x; x[4 * q + 1] = v4.y; x[4 * q + 2] = v4.z; x[4 * q + 3] = v4.w;
-            }
-            const float4 t4 = __ldg(r4 + RW / 4 - 1);
-            logp_old = t4.x; adv = t4.y; val_old = t4.z; act = __float_as_int(t4.w);
-        }
+    // P0: layer 1 of tile `k` from record `rc` into buffer k & 1, then (thread 0) the forward GEMM
+    auto phase0 = [&](const TcRecord<OW>& rc, uint32_t k) {
+        const uint32_t buf = k & 1u;
         {
             float h[64];
             const float* w1 = sW1 + net * H * OW;
@@ -145,23 +166,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                 const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int k = 4 * k4 + j;
+                    const int kk = 4 * k4 + j;
                     float z = bv[j];
 #pragma unroll
                     for (int q = 0; q < OW / 4; ++q) {
-                        const float4 w = *reinterpret_cast<const float4*>(w1 + k * OW + 4 * q);
-                        z = fmaf(x[4 * q + 3], w.w, fmaf(x[4 * q + 2], w.z, fmaf(x[4 * q + 1], w.y, fmaf(x[4 * q], w.x, z))));
+                        const float4 w = *reinterpret_cast<const float4*>(w1 + kk * OW + 4 * q);
+                        z = fmaf(rc.x[4 * q + 3], w.w, fmaf(rc.x[4 * q + 2], w.z, fmaf(rc.x[4 * q + 1], w.y, fmaf(rc.x[4 * q], w.x, z))));
                     }
-                    h[k] = tanh_fast(z);
+                    h[kk] = tanh_mufu(z);
                 }
             }
-            umma::store_row_sw128(tH1 + net * 16384, r, h);
+            umma::store_row_sw128(tH1 + buf * 32768 + net * 16384, r, h);
         }
         if (net == 0) {   // [obs | 1 | 0...] row of the NS16 tile (B operand of the dW1/db1 and db2 GEMMs)
             float o16[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o16[i] = i < O ? x[i] : (i == O ? 1.0f : 0.0f);
-            umma::store_row_ns16(tOBSb, TC_TILE, r, o16);
+            for (int i = 0; i < 16; ++i) o16[i] = i < O ? rc.x[i < OW ? i : 0] : (i == O ? 1.0f : 0.0f);
+            umma::store_row_ns16(tOBS + buf * 4096, TC_TILE, r, o16);
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
@@ -172,35 +193,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
             for (int n2 = 0; n2 < 2; ++n2)
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb)
-                    umma::mma(tmem + C_Z + n2 * 64, umma::make_desc(aH1 + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
+                    umma::mma(tmem + C_ZF + n2 * 64,
+                              umma::make_desc(aH1 + buf * 32768 + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
                               umma::make_desc(aW2 + n2 * 8192 + kb * 32, 16, 1024, umma::LAYOUT_SW128), ID_FWD, kb > 0);
             umma::commit(bars + 1);
         }
+    };
+
+    phase0(rec_next, 0);
+    TcRecord<OW> rec_cur = rec_next;
+    tc_load_record<OW, OP, RW>(rec_next, g, blockIdx.x + gridDim.x, ntiles, r);
+
+    for (uint32_t k = 0; k < nmy; ++k) {
+        const uint32_t par = k & 1u;
+
+        // ================= X(k): heads, loss, output gradients, dz2 =================
         mbar_wait(bars + 1, par);
         umma::fence_after_sync();
-
-        // ================= P1: heads, loss, output gradients, dz2 =================
         {
             float h[64];
-            ld64(trow + C_Z + net * 64, h);
+            ld64(trow + C_ZF + net * 64, h);
             const float* b2 = sB2 + net * H;
 #pragma unroll
             for (int k4 = 0; k4 < 16; ++k4) {
                 const float4 bb = *reinterpret_cast<const float4*>(b2 + 4 * k4);
-                h[4 * k4 + 0] = tanh_fast(h[4 * k4 + 0] + bb.x);
-                h[4 * k4 + 1] = tanh_fast(h[4 * k4 + 1] + bb.y);
-                h[4 * k4 + 2] = tanh_fast(h[4 * k4 + 2] + bb.z);
-                h[4 * k4 + 3] = tanh_fast(h[4 * k4 + 3] + bb.w);
+                h[4 * k4 + 0] = tanh_mufu(h[4 * k4 + 0] + bb.x);
+                h[4 * k4 + 1] = tanh_mufu(h[4 * k4 + 1] + bb.y);
+                h[4 * k4 + 2] = tanh_mufu(h[4 * k4 + 2] + bb.z);
+                h[4 * k4 + 3] = tanh_mufu(h[4 * k4 + 3] + bb.w);
             }
             umma::store_row_sw128(tH2 + net * 16384, r, h);
 
-            constexpr int NO = A;                  // head outputs handled by an actor thread; critic uses slot 0
-            float out[NO];
+            float out[A];
             const int wrow0 = net == 0 ? 0 : A;    // first head row of this net in sW4 / sB4
 #pragma unroll
-            for (int a = 0; a < NO; ++a) out[a] = 0.0f;
+            for (int a = 0; a < A; ++a) out[a] = 0.0f;
 #pragma unroll
-            for (int a = 0; a < NO; ++a) {
+            for (int a = 0; a < A; ++a) {
                 if (net == 0 || a == 0) {
                     const float* w = sW4 + (wrow0 + a) * H;
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -215,10 +244,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                     out[a] = (s0 + s1) + (s2 + s3) + sB4[wrow0 + a];
                 }
             }
-            float d[NO];
+            float d[A];
 #pragma unroll
-            for (int a = 0; a < NO; ++a) d[a] = 0.0f;
-            if (valid) {
+            for (int a = 0; a < A; ++a) d[a] = 0.0f;
+            if (rec_cur.valid) {
                 if (net == 0) {
                     float m = out[0];
 #pragma unroll
@@ -234,10 +263,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                         lp[a] = out[a] - lse;
                         p[a] = expf(lp[a]);
                         ent -= p[a] * lp[a];
-                        if (a == act) new_logp = lp[a];
+                        if (a == rec_cur.act) new_logp = lp[a];
                     }
-                    const float nadv = (adv - adv_mean) / (adv_std + 1e-8f);
-                    const float logratio = new_logp - logp_old;
+                    const float nadv = (rec_cur.adv - adv_mean) / (adv_std + 1e-8f);
+                    const float logratio = new_logp - rec_cur.logp_old;
                     const float ratio = expf(logratio);
                     const float pg1 = -nadv * ratio;
                     const float pg2 = -nadv * fminf(fmaxf(ratio, 1.0f - g.clip_coef), 1.0f + g.clip_coef);
@@ -248,17 +277,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                     lsum[4] += fabsf(ratio - 1.0f) > g.clip_coef ? 1.0f : 0.0f;
 #pragma unroll
                     for (int a = 0; a < A; ++a) {
-                        const float onehot = a == act ? 1.0f : 0.0f;
+                        const float onehot = a == rec_cur.act ? 1.0f : 0.0f;
                         d[a] = inv_m * (dpg * (onehot - p[a]) + g.ent_coef * p[a] * (lp[a] + ent));
                         gb4[a] += d[a];
                     }
                 } else {
                     const float v = out[0];
-                    const float ret = adv + val_old;
+                    const float ret = rec_cur.adv + rec_cur.val_old;
                     const float vd = v - ret;
                     const float vu = vd * vd;
-                    const float vdiff = v - val_old;
-                    const float vc = val_old + fminf(fmaxf(vdiff, -g.clip_coef), g.clip_coef);
+                    const float vdiff = v - rec_cur.val_old;
+                    const float vc = rec_cur.val_old + fminf(fmaxf(vdiff, -g.clip_coef), g.clip_coef);
                     const float vcd = vc - ret;
                     const float vcl = vcd * vcd;
                     lsum[1] += fmaxf(vu, vcl);
@@ -283,7 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
             for (int k4 = 0; k4 < 16; ++k4) {
                 float dh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int a = 0; a < NO; ++a) {
+                for (int a = 0; a < A; ++a) {
                     if (net == 0 || a == 0) {
                         const float4 ww = *reinterpret_cast<const float4*>(sW4 + (wrow0 + a) * H + 4 * k4);
                         dh[0] = fmaf(d[a], ww.x, dh[0]); dh[1] = fmaf(d[a], ww.y, dh[1]);
@@ -293,7 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) h[4 * k4 + j] = dh[j] * fmaf(-h[4 * k4 + j], h[4 * k4 + j], 1.0f);
             }
-            if (it > 0) mbar_wait(bars + 3, (it - 1) & 1u);   // previous tile's dW1 GEMM has finished reading tDZ
+            if (k > 0) mbar_wait(bars + 3, (k - 1) & 1u);   // w1(k-1) has finished reading tDZ and tOBS[(k+1)&1]
             umma::store_row_sw128(tDZ + net * 16384, r, h);
         }
         umma::fence_proxy_async();
@@ -301,35 +330,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         __syncthreads();
         if (tid == 0) {
             umma::fence_after_sync();
-            const uint32_t acc = it > 0 ? 1u : 0u;
+            const uint32_t acc = k > 0 ? 1u : 0u;
+            const uint32_t h1b = aH1 + par * 32768, obsb = aOBS + par * 4096;
 #pragma unroll
             for (int n2 = 0; n2 < 2; ++n2)
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb)
-                    umma::mma(tmem + C_Z + n2 * 64, umma::make_desc(aDZ + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
+                    umma::mma(tmem + C_DH + n2 * 64, umma::make_desc(aDZ + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
                               umma::make_desc(aW2 + n2 * 8192 + kb * 2048, 8192, 1024, umma::LAYOUT_SW128), ID_DH1, kb > 0);
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb)
                 umma::mma(tmem + C_W2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
-                          umma::make_desc(aH1 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128), ID_W2, acc | (kb > 0));
+                          umma::make_desc(h1b + kb * 2048, 16384, 1024, umma::LAYOUT_SW128), ID_W2, acc | (kb > 0));
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb)
                 umma::mma(tmem + C_B2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
-                          umma::make_desc(aOBS + par * 4096 + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
+                          umma::make_desc(obsb + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb)
                 umma::mma(tmem + C_W4, umma::make_desc(aH2 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
                           umma::make_desc(aDOUT + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
             umma::commit(bars + 2);
         }
+
+        // ================= Y(k): layer 1 + forward GEMM of the next tile (hides bwd(k)) =================
+        if (k + 1 < nmy) {
+            phase0(rec_next, k + 1);
+            rec_cur = rec_next;
+            tc_load_record<OW, OP, RW>(rec_next, g, blockIdx.x + (k + 2) * gridDim.x, ntiles, r);
+        }
+
+        // ================= Z(k): dz1 = dh1 * (1 - h1^2) (hides fwd(k+1)) =================
         mbar_wait(bars + 2, par);
         umma::fence_after_sync();
-
-        // ================= P2: dz1 = dh1 * (1 - h1^2) =================
         {
             float dh[64];
-            ld64(trow + C_Z + net * 64, dh);
-            const unsigned char* h1row = tH1 + net * 16384;
+            ld64(trow + C_DH + net * 64, dh);
+            const unsigned char* h1row = tH1 + par * 32768 + net * 16384;
             unsigned char* dzrow = tDZ + net * 16384;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {   // 16-byte chunk at a time: h1 (bf16) in, dz1 (bf16) out
@@ -351,7 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         __syncthreads();
         if (tid == 0) {
             umma::fence_after_sync();
-            const uint32_t acc = it > 0 ? 1u : 0u;
+            const uint32_t acc = k > 0 ? 1u : 0u;
 #pragma unroll
             for (int kb = 0; kb < 8; ++kb)
                 umma::mma(tmem + C_W1, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
@@ -359,7 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
             umma::commit(bars + 3);
         }
     }
-    if (it > 0) mbar_wait(bars + 3, (it - 1) & 1u);
+    mbar_wait(bars + 3, (nmy - 1) & 1u);
     umma::fence_after_sync();
 
     // ================= epilogue: this CTA's partial gradient, canonical layout =================
@@ -396,9 +433,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     {
         float vals[9] = {lsum[0], lsum[1], lsum[2], lsum[3], lsum[4], gb4[0], gb4[1], gb4[2], gb4[3]};
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const float s = warp_sum(vals[k]);
-            if (lane == 0) red[warp * 12 + k] = s;
+        for (int q = 0; q < 9; ++q) {
+            const float s = warp_sum(vals[q]);
+            if (lane == 0) red[warp * 12 + q] = s;
         }
     }
     umma::fence_before_sync();
