@@ -2,8 +2,9 @@
 // deep_rl/ppo.py:159-190.  Same inputs, outputs and per-CTA partial-gradient format as ppo_grad_kernel
 // (update_ops.cu); operands of the GEMMs are bf16, accumulation is fp32 in tensor memory.
 //
-// One persistent CTA per SM, 256 threads.  A tile is 128 samples = the 128 TMEM lanes; thread (warp w, lane l)
-// owns sample row r = 32*(w&3)+l of net (w>>2) (0 = actor trunk, 1 = critic trunk).  Work per tile k:
+// One persistent CTA per SM: 16 compute warps + 1 MMA-issuer warp.  A tile is 128 samples = the 128 TMEM lanes;
+// compute thread (warp w, lane l) owns sample row r = 32*(w&3)+l, net (w>>3) (0 = actor trunk, 1 = critic trunk) and
+// hidden units [32*((w>>2)&1), +32) of that net, i.e. four threads share a row.  Work per tile k:
 //   P0(k)  layer 1 on CUDA cores from the prefetched 32-byte record (K = 4/6 is degenerate for UMMA),
 //          h1 -> bf16 SW128 tile, [obs|1] -> NS16 tile
 //   MMA    fwd(k):  z2 = h1 . W2^T                      (per net M128 N64 K64, A/B K-major)
@@ -14,10 +15,12 @@
 //                   db2 += dz2^T . [obs|1]   dW4 += h2^T . dout          (M128 N16 K128)
 //   P2(k)  tcgen05.ld dh1, dz1 = dh1 * (1 - h1^2) -> bf16 tile
 //   MMA    w1(k):   [dW1|db1] += dz1^T . [obs|1]        (M128 N16 K128)
-// The loop is software-pipelined so that no thread ever waits for a GEMM it has just issued:
-//   X(k): wait fwd(k), P1(k), issue bwd(k)   Y(k): P0(k+1), issue fwd(k+1)   Z(k): wait bwd(k), P2(k), issue w1(k)
-// (h1 and [obs|1] tiles are double-buffered, z2 and dh1 have separate TMEM columns, records are prefetched one
-// tile ahead).  All weight-gradient accumulators live in TMEM for the whole kernel (432 of 512 columns used) and
+// The loop is software-pipelined and warp-specialised so that no compute warp waits for a GEMM it has just
+// handed over, and no CTA-wide barrier sits in the loop:
+//   X(k): wait fwd(k), P1(k), hand bwd(k)   Y(k): P0(k+1), hand fwd(k+1)   Z(k): wait bwd(k), P2(k), hand w1(k)
+// "hand" = fence.proxy.async + bar.arrive on a named barrier; the issuer warp bar.syncs on it, issues the
+// tcgen05.mma group and commits to an mbarrier the compute warps wait on.  h1 and [obs|1] tiles are double-buffered,
+// z2 and dh1 have separate TMEM columns, records are prefetched one tile ahead and their indices two tiles ahead.  All weight-gradient accumulators live in TMEM for the whole kernel (432 of 512 columns used) and
 // are written once, as this CTA's partial gradient, at the end.
 #include "drl_pack.cuh"
 #include "drl_umma.cuh"
@@ -25,7 +28,9 @@
 
 namespace drl {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_COMPUTE = 512;           // 16 compute warps
+constexpr int TC_THREADS = TC_COMPUTE + 32;  // + the MMA-issuer warp
+constexpr int HU = 32;                     // hidden units per compute thread
 constexpr int TC_TILE = 128;
 // TMEM columns
 constexpr uint32_t C_ZF = 0, C_DH = 128, C_W2 = 256, C_B2 = 384, C_W4 = 400, C_W1 = 416, TC_COLS = 512;
@@ -41,17 +46,10 @@ struct TcSmem {
     static constexpr int OFF_OBS = OFF_DZ + 32768;     // two NS16 buffers (tile parity)
     static constexpr int OFF_DOUT = OFF_OBS + 8192;    // one NS16 buffer
     static constexpr int OFF_BAR = OFF_DOUT + 4096;    // 4 mbarriers + TMEM slot
-    static constexpr int OFF_RED = OFF_BAR + 64;
-    static constexpr int TOTAL = OFF_RED + 8 * 12 * 4 + 1024;   // + alignment slack
+    static constexpr int OFF_XCH = OFF_BAR + 64;       // head partial sums [net][half][A][128 rows] fp32
+    static constexpr int OFF_RED = OFF_XCH + 2 * 2 * 4 * 128 * 4;
+    static constexpr int TOTAL = OFF_RED + 16 * 12 * 4 + 1024;   // + alignment slack
 };
-
-__device__ __forceinline__ void ld64(uint32_t taddr, float (&v)[64]) {
-    float lo[32], hi[32];
-    umma::ld32(taddr, lo);
-    umma::ld32(taddr + 32, hi);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { v[i] = lo[i]; v[32 + i] = hi[i]; }
-}
 
 // tanh on the SFU (one MUFU op, |abs err| ~ 5e-4): below the bf16 rounding the activations get anyway
 __device__ __forceinline__ float tanh_mufu(float x) {
@@ -59,6 +57,14 @@ __device__ __forceinline__ float tanh_mufu(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+enum : uint32_t { BAR_FWD = 1, BAR_BWD = 2, BAR_W1 = 3, BAR_PAIR0 = 4 };   // named barriers (0 = __syncthreads)
 
 template <int OW>
 struct TcRecord {       // one sample record, held in registers between its prefetch and its use
@@ -68,17 +74,22 @@ struct TcRecord {       // one sample record, held in registers between its pref
     bool valid;
 };
 
+// sample id of row r of this CTA's tile `tile` (0xFFFFFFFF = padding row)
+__device__ __forceinline__ uint32_t tc_sample_index(const GradArgs& g, uint32_t tile, uint32_t ntiles, int r) {
+    const uint32_t pos = tile * TC_TILE + (uint32_t)r;
+    if (tile >= ntiles || pos >= g.mb_count) return 0xFFFFFFFFu;
+    const uint32_t i = g.mb_start + pos;
+    return g.idx ? __ldg(g.idx + i) : i;
+}
+
 template <int OW, int OP, int RW>
-__device__ __forceinline__ void tc_load_record(TcRecord<OW>& rc, const GradArgs& g, uint32_t tile, uint32_t ntiles, int r) {
+__device__ __forceinline__ void tc_load_record(TcRecord<OW>& rc, const GradArgs& g, uint32_t s) {
 #pragma unroll
     for (int i = 0; i < OW; ++i) rc.x[i] = 0.0f;
     rc.logp_old = 0.f; rc.adv = 0.f; rc.val_old = 0.f; rc.act = 0;
-    const uint32_t pos = tile * TC_TILE + (uint32_t)r;
-    rc.valid = tile < ntiles && pos < g.mb_count;
+    rc.valid = s != 0xFFFFFFFFu;
     if (rc.valid) {
-        const uint32_t i = g.mb_start + pos;
-        const size_t s = g.idx ? g.idx[i] : i;
-        const float4* r4 = reinterpret_cast<const float4*>(g.rec + s * RW);
+        const float4* r4 = reinterpret_cast<const float4*>(g.rec + (size_t)s * RW);
 #pragma unroll
         for (int q = 0; q < OP / 4; ++q) {
             const float4 v4 = __ldg(r4 + q);
@@ -86,6 +97,19 @@ __device__ __forceinline__ void tc_load_record(TcRecord<OW>& rc, const GradArgs&
         }
         const float4 t4 = __ldg(r4 + RW / 4 - 1);
         rc.logp_old = t4.x; rc.adv = t4.y; rc.val_old = t4.z; rc.act = __float_as_int(t4.w);
+    }
+}
+
+// four 16-byte chunks (32 bf16) of row `row` of a SW128 tile, starting at chunk c0
+__device__ __forceinline__ void store_half_row_sw128(unsigned char* tile, int row, int c0, const float (&v)[HU]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 q;
+        q.x = umma::pack_bf16(v[8 * c + 0], v[8 * c + 1]);
+        q.y = umma::pack_bf16(v[8 * c + 2], v[8 * c + 3]);
+        q.z = umma::pack_bf16(v[8 * c + 4], v[8 * c + 5]);
+        q.w = umma::pack_bf16(v[8 * c + 6], v[8 * c + 7]);
+        *reinterpret_cast<uint4*>(tile + umma::sw128_off(row, c0 + c)) = q;
     }
 }
 
@@ -109,17 +133,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     unsigned char* tDOUT = sm + S::OFF_DOUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd, 2 bwd, 3 w1
     uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 4);
+    float* xch = reinterpret_cast<float*>(sm + S::OFF_XCH);
     float* red = reinterpret_cast<float*>(sm + S::OFF_RED);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int net = warp >> 2;
-    const int r = (warp & 3) * 32 + lane;
+    const bool is_mma_warp = warp == TC_COMPUTE / 32;
+    const int rw = warp & 3, half = (warp >> 2) & 1, net = (warp >> 3) & 1;
+    const int r = rw * 32 + lane;
+    const int u0 = half * HU;
     const uint32_t ntiles = (g.mb_count + TC_TILE - 1) / TC_TILE;
     const uint32_t nmy = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles of this CTA (>= 1)
 
-    // ---- prologue: first record in flight, barriers, TMEM, weights by TMA bulk copy ----
-    TcRecord<OW> rec_next;
-    tc_load_record<OW, OP, RW>(rec_next, g, blockIdx.x, ntiles, r);
+    // ---- prologue: barriers, TMEM, weights by TMA bulk copy ----
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
@@ -138,30 +163,102 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         }
     }
     const uint32_t tmem = *slot;
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this thread's TMEM lane
+
+    if (is_mma_warp) {
+        // =========================== MMA-issuer warp ===========================
+        const uint32_t aW2 = smem_u32(tW2), aH1 = smem_u32(tH1), aH2 = smem_u32(tH2), aDZ = smem_u32(tDZ);
+        const uint32_t aOBS = smem_u32(tOBS), aDOUT = smem_u32(tDOUT);
+        constexpr uint32_t ID_FWD = umma::make_idesc(128, 64, false, false);
+        constexpr uint32_t ID_DH1 = umma::make_idesc(128, 64, false, true);
+        constexpr uint32_t ID_W2 = umma::make_idesc(128, 128, true, true);
+        constexpr uint32_t ID_N16 = umma::make_idesc(128, 16, true, true);
+        mbar_wait(bars, 0);   // W2 tiles have landed
+        auto issue_fwd = [&](uint32_t k) {
+            const uint32_t h1b = aH1 + (k & 1u) * 32768;
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+                    umma::mma(tmem + C_ZF + n2 * 64, umma::make_desc(h1b + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
+                              umma::make_desc(aW2 + n2 * 8192 + kb * 32, 16, 1024, umma::LAYOUT_SW128), ID_FWD, kb > 0);
+            umma::commit(bars + 1);
+        };
+        named_bar_sync(BAR_FWD, TC_THREADS);
+        umma::fence_after_sync();
+        if (lane == 0) issue_fwd(0);
+        __syncwarp();
+        for (uint32_t k = 0; k < nmy; ++k) {
+            const uint32_t par = k & 1u, acc = k > 0 ? 1u : 0u;
+            named_bar_sync(BAR_BWD, TC_THREADS);
+            umma::fence_after_sync();
+            if (lane == 0) {
+                const uint32_t h1b = aH1 + par * 32768, obsb = aOBS + par * 4096;
+#pragma unroll
+                for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb)
+                        umma::mma(tmem + C_DH + n2 * 64, umma::make_desc(aDZ + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
+                                  umma::make_desc(aW2 + n2 * 8192 + kb * 2048, 8192, 1024, umma::LAYOUT_SW128), ID_DH1, kb > 0);
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb)
+                    umma::mma(tmem + C_W2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                              umma::make_desc(h1b + kb * 2048, 16384, 1024, umma::LAYOUT_SW128), ID_W2, acc | (kb > 0));
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb)
+                    umma::mma(tmem + C_B2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                              umma::make_desc(obsb + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb)
+                    umma::mma(tmem + C_W4, umma::make_desc(aH2 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                              umma::make_desc(aDOUT + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
+                umma::commit(bars + 2);
+            }
+            __syncwarp();
+            if (k + 1 < nmy) {
+                named_bar_sync(BAR_FWD, TC_THREADS);
+                umma::fence_after_sync();
+                if (lane == 0) issue_fwd(k + 1);
+                __syncwarp();
+            }
+            named_bar_sync(BAR_W1, TC_THREADS);
+            umma::fence_after_sync();
+            if (lane == 0) {
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb)
+                    umma::mma(tmem + C_W1, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                              umma::make_desc(aOBS + par * 4096 + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
+                umma::commit(bars + 3);
+            }
+            __syncwarp();
+        }
+        umma::fence_before_sync();
+        __syncthreads();           // epilogue barrier of the compute warps
+        return;
+    }
+
+    // =========================== compute warps ===========================
+    const uint32_t trow = tmem + ((uint32_t)(rw * 32) << 16);   // this thread's TMEM lane
     const float adv_mean = g.adv_stats[0], adv_std = g.adv_stats[1];
     const float inv_m = 1.0f / (float)g.mb_count;
-    mbar_wait(bars, 0);
-
-    const uint32_t aW2 = smem_u32(tW2), aH1 = smem_u32(tH1), aH2 = smem_u32(tH2), aDZ = smem_u32(tDZ);
-    const uint32_t aOBS = smem_u32(tOBS), aDOUT = smem_u32(tDOUT);
-    constexpr uint32_t ID_FWD = umma::make_idesc(128, 64, false, false);
-    constexpr uint32_t ID_DH1 = umma::make_idesc(128, 64, false, true);
-    constexpr uint32_t ID_W2 = umma::make_idesc(128, 128, true, true);
-    constexpr uint32_t ID_N16 = umma::make_idesc(128, 16, true, true);
-
-    float lsum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // pg, v, entropy, kl, clipfrac partial sums
+    const int wrow0 = net == 0 ? 0 : A;          // first head row of this net in sW4 / sB4
+    const int nheads = net == 0 ? A : 1;
+    float lsum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // pg, v, entropy, kl, clipfrac partial sums (half-0 threads only)
     float gb4[4] = {0.f, 0.f, 0.f, 0.f};         // head-bias gradients: actor slots 0..A-1, critic slot 3
 
-    // P0: layer 1 of tile `k` from record `rc` into buffer k & 1, then (thread 0) the forward GEMM
+    TcRecord<OW> rec_cur, rec_next;
+    tc_load_record<OW, OP, RW>(rec_cur, g, tc_sample_index(g, blockIdx.x, ntiles, r));
+    uint32_t s_next = tc_sample_index(g, blockIdx.x + gridDim.x, ntiles, r);
+    mbar_wait(bars, 0);
+
+    // P0: layer 1 (this thread's 32 units) of tile k from record rc into buffer k & 1, then hand fwd(k)
     auto phase0 = [&](const TcRecord<OW>& rc, uint32_t k) {
         const uint32_t buf = k & 1u;
         {
-            float h[64];
-            const float* w1 = sW1 + net * H * OW;
-            const float* b1 = sB1 + net * H;
+            float h[HU];
+            const float* w1 = sW1 + (net * H + u0) * OW;
+            const float* b1 = sB1 + net * H + u0;
 #pragma unroll
-            for (int k4 = 0; k4 < 16; ++k4) {
+            for (int k4 = 0; k4 < HU / 4; ++k4) {
                 const float4 bb = *reinterpret_cast<const float4*>(b1 + 4 * k4);
                 const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -176,33 +273,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                     h[kk] = tanh_mufu(z);
                 }
             }
-            umma::store_row_sw128(tH1 + buf * 32768 + net * 16384, r, h);
+            store_half_row_sw128(tH1 + buf * 32768 + net * 16384, r, half * 4, h);
         }
-        if (net == 0) {   // [obs | 1 | 0...] row of the NS16 tile (B operand of the dW1/db1 and db2 GEMMs)
+        if (warp < 4) {   // [obs | 1 | 0...] row of the NS16 tile (B operand of the dW1/db1 and db2 GEMMs)
             float o16[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) o16[i] = i < O ? rc.x[i < OW ? i : 0] : (i == O ? 1.0f : 0.0f);
             umma::store_row_ns16(tOBS + buf * 4096, TC_TILE, r, o16);
         }
         umma::fence_proxy_async();
-        umma::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-#pragma unroll
-            for (int n2 = 0; n2 < 2; ++n2)
-#pragma unroll
-                for (int kb = 0; kb < 4; ++kb)
-                    umma::mma(tmem + C_ZF + n2 * 64,
-                              umma::make_desc(aH1 + buf * 32768 + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
-                              umma::make_desc(aW2 + n2 * 8192 + kb * 32, 16, 1024, umma::LAYOUT_SW128), ID_FWD, kb > 0);
-            umma::commit(bars + 1);
-        }
+        named_bar_arrive(BAR_FWD, TC_THREADS);
     };
 
-    phase0(rec_next, 0);
-    TcRecord<OW> rec_cur = rec_next;
-    tc_load_record<OW, OP, RW>(rec_next, g, blockIdx.x + gridDim.x, ntiles, r);
+    phase0(rec_cur, 0);
+    tc_load_record<OW, OP, RW>(rec_next, g, s_next);
+    s_next = tc_sample_index(g, blockIdx.x + 2 * gridDim.x, ntiles, r);
 
     for (uint32_t k = 0; k < nmy; ++k) {
         const uint32_t par = k & 1u;
@@ -211,37 +296,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         mbar_wait(bars + 1, par);
         umma::fence_after_sync();
         {
-            float h[64];
-            ld64(trow + C_ZF + net * 64, h);
-            const float* b2 = sB2 + net * H;
+            float h[HU];
+            umma::ld32(trow + C_ZF + net * 64 + u0, h);
+            const float* b2 = sB2 + net * H + u0;
 #pragma unroll
-            for (int k4 = 0; k4 < 16; ++k4) {
+            for (int k4 = 0; k4 < HU / 4; ++k4) {
                 const float4 bb = *reinterpret_cast<const float4*>(b2 + 4 * k4);
                 h[4 * k4 + 0] = tanh_mufu(h[4 * k4 + 0] + bb.x);
                 h[4 * k4 + 1] = tanh_mufu(h[4 * k4 + 1] + bb.y);
                 h[4 * k4 + 2] = tanh_mufu(h[4 * k4 + 2] + bb.z);
                 h[4 * k4 + 3] = tanh_mufu(h[4 * k4 + 3] + bb.w);
             }
-            umma::store_row_sw128(tH2 + net * 16384, r, h);
+            store_half_row_sw128(tH2 + net * 16384, r, half * 4, h);
 
-            float out[A];
-            const int wrow0 = net == 0 ? 0 : A;    // first head row of this net in sW4 / sB4
-#pragma unroll
-            for (int a = 0; a < A; ++a) out[a] = 0.0f;
+            // head partial sums over this thread's 32 units, exchanged with the thread owning the other 32
+            float ps[A];
 #pragma unroll
             for (int a = 0; a < A; ++a) {
-                if (net == 0 || a == 0) {
-                    const float* w = sW4 + (wrow0 + a) * H;
+                ps[a] = 0.0f;
+                if (a < nheads) {
+                    const float* w = sW4 + (wrow0 + a) * H + u0;
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                    for (int k4 = 0; k4 < 16; ++k4) {
+                    for (int k4 = 0; k4 < HU / 4; ++k4) {
                         const float4 ww = *reinterpret_cast<const float4*>(w + 4 * k4);
                         s0 = fmaf(h[4 * k4 + 0], ww.x, s0);
                         s1 = fmaf(h[4 * k4 + 1], ww.y, s1);
                         s2 = fmaf(h[4 * k4 + 2], ww.z, s2);
                         s3 = fmaf(h[4 * k4 + 3], ww.w, s3);
                     }
-                    out[a] = (s0 + s1) + (s2 + s3) + sB4[wrow0 + a];
+                    ps[a] = (s0 + s1) + (s2 + s3);
+                    xch[((net * 2 + half) * 4 + a) * TC_TILE + r] = ps[a];
+                }
+            }
+            named_bar_sync(BAR_PAIR0 + net * 4 + rw, 64);
+            float out[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                out[a] = 0.0f;
+                if (a < nheads) {
+                    const float po = xch[((net * 2 + (half ^ 1)) * 4 + a) * TC_TILE + r];
+                    const float lo = half == 0 ? ps[a] : po, hi = half == 0 ? po : ps[a];
+                    out[a] = (lo + hi) + sB4[wrow0 + a];      // identical in both threads of the pair
                 }
             }
             float d[A];
@@ -271,15 +367,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                     const float pg1 = -nadv * ratio;
                     const float pg2 = -nadv * fminf(fmaxf(ratio, 1.0f - g.clip_coef), 1.0f + g.clip_coef);
                     const float dpg = pg1 >= pg2 ? pg1 : 0.0f;
-                    lsum[0] += fmaxf(pg1, pg2);
-                    lsum[2] += ent;
-                    lsum[3] += (ratio - 1.0f) - logratio;
-                    lsum[4] += fabsf(ratio - 1.0f) > g.clip_coef ? 1.0f : 0.0f;
+                    if (half == 0) {
+                        lsum[0] += fmaxf(pg1, pg2);
+                        lsum[2] += ent;
+                        lsum[3] += (ratio - 1.0f) - logratio;
+                        lsum[4] += fabsf(ratio - 1.0f) > g.clip_coef ? 1.0f : 0.0f;
+                    }
 #pragma unroll
                     for (int a = 0; a < A; ++a) {
                         const float onehot = a == rec_cur.act ? 1.0f : 0.0f;
                         d[a] = inv_m * (dpg * (onehot - p[a]) + g.ent_coef * p[a] * (lp[a] + ent));
-                        gb4[a] += d[a];
+                        if (half == 0) gb4[a] += d[a];
                     }
                 } else {
                     const float v = out[0];
@@ -290,14 +388,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                     const float vc = rec_cur.val_old + fminf(fmaxf(vdiff, -g.clip_coef), g.clip_coef);
                     const float vcd = vc - ret;
                     const float vcl = vcd * vcd;
-                    lsum[1] += fmaxf(vu, vcl);
                     const float gcl = (vdiff >= -g.clip_coef && vdiff <= g.clip_coef) ? vcd : 0.0f;
                     const float gv = vu > vcl ? vd : (vcl > vu ? gcl : 0.5f * (vd + gcl));
                     d[0] = g.vf_coef * gv * inv_m;
-                    gb4[3] += d[0];
+                    if (half == 0) { lsum[1] += fmaxf(vu, vcl); gb4[3] += d[0]; }
                 }
             }
-            {   // dout row: actor -> columns 0..A-1 (chunk 0), critic -> column 8 (chunk 1)
+            if (half == 0) {   // dout row: actor -> columns 0..A-1 (chunk 0), critic -> column 8 (chunk 1)
                 uint4 q = make_uint4(0u, 0u, 0u, 0u);
                 if (net == 0) {
                     q.x = umma::pack_bf16(d[0], d[1]);
@@ -309,12 +406,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
             }
             // dz2 = (dout . W4) * (1 - h2^2), in place
 #pragma unroll
-            for (int k4 = 0; k4 < 16; ++k4) {
+            for (int k4 = 0; k4 < HU / 4; ++k4) {
                 float dh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int a = 0; a < A; ++a) {
-                    if (net == 0 || a == 0) {
-                        const float4 ww = *reinterpret_cast<const float4*>(sW4 + (wrow0 + a) * H + 4 * k4);
+                    if (a < nheads) {
+                        const float4 ww = *reinterpret_cast<const float4*>(sW4 + (wrow0 + a) * H + u0 + 4 * k4);
                         dh[0] = fmaf(d[a], ww.x, dh[0]); dh[1] = fmaf(d[a], ww.y, dh[1]);
                         dh[2] = fmaf(d[a], ww.z, dh[2]); dh[3] = fmaf(d[a], ww.w, dh[3]);
                     }
@@ -323,54 +420,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                 for (int j = 0; j < 4; ++j) h[4 * k4 + j] = dh[j] * fmaf(-h[4 * k4 + j], h[4 * k4 + j], 1.0f);
             }
             if (k > 0) mbar_wait(bars + 3, (k - 1) & 1u);   // w1(k-1) has finished reading tDZ and tOBS[(k+1)&1]
-            umma::store_row_sw128(tDZ + net * 16384, r, h);
+            store_half_row_sw128(tDZ + net * 16384, r, half * 4, h);
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            const uint32_t acc = k > 0 ? 1u : 0u;
-            const uint32_t h1b = aH1 + par * 32768, obsb = aOBS + par * 4096;
-#pragma unroll
-            for (int n2 = 0; n2 < 2; ++n2)
-#pragma unroll
-                for (int kb = 0; kb < 4; ++kb)
-                    umma::mma(tmem + C_DH + n2 * 64, umma::make_desc(aDZ + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
-                              umma::make_desc(aW2 + n2 * 8192 + kb * 2048, 8192, 1024, umma::LAYOUT_SW128), ID_DH1, kb > 0);
-#pragma unroll
-            for (int kb = 0; kb < 8; ++kb)
-                umma::mma(tmem + C_W2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
-                          umma::make_desc(h1b + kb * 2048, 16384, 1024, umma::LAYOUT_SW128), ID_W2, acc | (kb > 0));
-#pragma unroll
-            for (int kb = 0; kb < 8; ++kb)
-                umma::mma(tmem + C_B2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
-                          umma::make_desc(obsb + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
-#pragma unroll
-            for (int kb = 0; kb < 8; ++kb)
-                umma::mma(tmem + C_W4, umma::make_desc(aH2 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
-                          umma::make_desc(aDOUT + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
-            umma::commit(bars + 2);
-        }
+        named_bar_arrive(BAR_BWD, TC_THREADS);
 
-        // ================= Y(k): layer 1 + forward GEMM of the next tile (hides bwd(k)) =================
+        // ================= Y(k): layer 1 of the next tile, hand fwd(k+1) (hides bwd(k)) =================
         if (k + 1 < nmy) {
             phase0(rec_next, k + 1);
             rec_cur = rec_next;
-            tc_load_record<OW, OP, RW>(rec_next, g, blockIdx.x + (k + 2) * gridDim.x, ntiles, r);
+            tc_load_record<OW, OP, RW>(rec_next, g, s_next);
+            s_next = tc_sample_index(g, blockIdx.x + (k + 3) * gridDim.x, ntiles, r);
         }
 
         // ================= Z(k): dz1 = dh1 * (1 - h1^2) (hides fwd(k+1)) =================
         mbar_wait(bars + 2, par);
         umma::fence_after_sync();
         {
-            float dh[64];
-            ld64(trow + C_DH + net * 64, dh);
+            float dh[HU];
+            umma::ld32(trow + C_DH + net * 64 + u0, dh);
             const unsigned char* h1row = tH1 + par * 32768 + net * 16384;
             unsigned char* dzrow = tDZ + net * 16384;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {   // 16-byte chunk at a time: h1 (bf16) in, dz1 (bf16) out
-                const uint32_t off = umma::sw128_off(r, c);
+            for (int c = 0; c < 4; ++c) {   // 16-byte chunk at a time: h1 (bf16) in, dz1 (bf16) out
+                const uint32_t off = umma::sw128_off(r, half * 4 + c);
                 const uint4 q = *reinterpret_cast<const uint4*>(h1row + off);
                 const float hv[8] = {umma::bf16_lo(q.x), umma::bf16_hi(q.x), umma::bf16_lo(q.y), umma::bf16_hi(q.y),
                                      umma::bf16_lo(q.z), umma::bf16_hi(q.z), umma::bf16_lo(q.w), umma::bf16_hi(q.w)};
@@ -385,24 +459,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            const uint32_t acc = k > 0 ? 1u : 0u;
-#pragma unroll
-            for (int kb = 0; kb < 8; ++kb)
-                umma::mma(tmem + C_W1, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
-                          umma::make_desc(aOBS + par * 4096 + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
-            umma::commit(bars + 3);
-        }
+        named_bar_arrive(BAR_W1, TC_THREADS);
     }
     mbar_wait(bars + 3, (nmy - 1) & 1u);
     umma::fence_after_sync();
 
     // ================= epilogue: this CTA's partial gradient, canonical layout =================
     float* part = g.grad_part + (size_t)blockIdx.x * g.ppad;
+    const int no = r >> 6, o = r & 63;                 // TMEM lane r = hidden unit o of net `no`
     if (warp < 4) {
-        const int no = r >> 6, o = r & 63;             // TMEM lane r = hidden unit o of net `no`
         const int base = no * P::C_ACTOR;
         float v16[16];
         umma::ld16(trow + C_B2, v16);
@@ -419,34 +484,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
             part[P::C_ACTOR + P::C_NET + o] = v16[8];                           // critic head
         }
     }
-    {   // dW2: the diagonal 64x64 blocks of the 128x128 accumulator
-        const int no = r >> 6, o = r & 63;
-        if (no == net) {   // warp-uniform
-            float v[64];
-            ld64(trow + C_W2 + net * 64, v);
-            float* dst = part + net * P::C_ACTOR + H * O + H + o * H;
+    if (no == net) {   // dW2: the diagonal 64x64 blocks of the 128x128 accumulator (warp-uniform branch)
+        float v[HU];
+        umma::ld32(trow + C_W2 + net * 64 + u0, v);
+        float* dst = part + net * P::C_ACTOR + H * O + H + o * H + u0;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) dst[i] = v[i];
-        }
+        for (int i = 0; i < HU; ++i) dst[i] = v[i];
     }
-    // loss partial sums and head-bias gradients: fold the 256 threads
+    // loss partial sums and head-bias gradients: fold the 512 compute threads
     {
         float vals[9] = {lsum[0], lsum[1], lsum[2], lsum[3], lsum[4], gb4[0], gb4[1], gb4[2], gb4[3]};
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
-            const float s = warp_sum(vals[q]);
-            if (lane == 0) red[warp * 12 + q] = s;
+            const float sv = warp_sum(vals[q]);
+            if (lane == 0) red[warp * 12 + q] = sv;
         }
     }
     umma::fence_before_sync();
     __syncthreads();
     if (tid < 9) {
-        float s = 0.0f;
+        float sv = 0.0f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w * 12 + tid];
-        if (tid < 5) g.loss_part[blockIdx.x * LOSS_TERMS + tid] = s;
-        else if (tid - 5 < A) part[P::C_NET + A * H + (tid - 5)] = s;              // actor head bias
-        else if (tid == 8) part[P::C_ACTOR + P::C_NET + H] = s;                    // critic head bias
+        for (int w = 0; w < TC_COMPUTE / 32; ++w) sv += red[w * 12 + tid];
+        if (tid < 5) g.loss_part[blockIdx.x * LOSS_TERMS + tid] = sv;
+        else if (tid - 5 < A) part[P::C_NET + A * H + (tid - 5)] = sv;              // actor head bias
+        else if (tid == 8) part[P::C_ACTOR + P::C_NET + H] = sv;                    // critic head bias
     }
     if (warp == 1) umma::tmem_dealloc(tmem, TC_COLS);
 }
