@@ -65,7 +65,7 @@ constexpr int STAT_PARTS = 64;       // partial-sum CTAs per minibatch in drl_ad
 constexpr int LOSS_TERMS = 8;
 
 struct WorkspaceLayout {
-    size_t counters, stat_partials, loss_partials, grad_partials, total;
+    size_t counters, stat_partials, loss_partials, grad_partials, debug, total;
     int ppad;
 };
 inline WorkspaceLayout workspace_layout(int64_t P) {
@@ -75,7 +75,8 @@ inline WorkspaceLayout workspace_layout(int64_t P) {
     w.stat_partials = 64;
     w.loss_partials = w.stat_partials + sizeof(double) * MAX_MINIBATCHES * STAT_PARTS * 2;
     w.grad_partials = w.loss_partials + sizeof(float) * MAX_GRAD_CTAS * LOSS_TERMS;
-    w.total = w.grad_partials + sizeof(float) * (size_t)MAX_GRAD_CTAS * w.ppad;
+    w.debug = w.grad_partials + sizeof(float) * (size_t)MAX_GRAD_CTAS * w.ppad;   // 4 KB of cycle stamps (DRL_TC_DEBUG=1)
+    w.total = w.debug + 4096;
     return w;
 }
 inline size_t workspace_bytes_for(int64_t P) { return workspace_layout(P).total; }

@@ -43,6 +43,13 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// true in exactly one lane of a converged warp; lets the compiler emit the tcgen05 sequence without a per-lane loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

@@ -15,6 +15,7 @@ struct GradArgs {
     float* grad_part;         // [gridDim.x][ppad]
     float* loss_part;         // [gridDim.x][LOSS_TERMS]
     int ppad;
+    long long* dbg;           // optional cycle stamps (diagnostics), else nullptr
 };
 
 // fixed-order fold of `grid` per-CTA partial gradients / loss sums (update_ops.cu)

@@ -16,13 +16,13 @@ drl_ep_log_t log_or_empty(const drl_ep_log_t* log);
 
 constexpr int RO_WARPS = 4;
 
-template <int KIND, int SUB>
+template <int KIND, int SUB, int TL>
 __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(drl_env_t env, const float* __restrict__ packed, int T,
                                                                 uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log) {
     using S = EnvSpec<KIND>;
     constexpr int O = S::O, A = S::A, OP = S::OP;
     using P = Packed<O, A>;
-    constexpr int EPW = TILE * SUB;                       // envs per warp
+    constexpr int EPW = TL * SUB;                         // envs per warp
     constexpr int WS = SUB * OBS_S + H1_S + SUB * OUT_S;  // per-warp scratch floats
 
     extern __shared__ __align__(128) float smem[];
@@ -57,17 +57,17 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(drl_env_t env, c
 #pragma unroll
                 for (int q = 0; q < OP / 4; ++q) o4[q] = make_float4(obs[4 * q], obs[4 * q + 1], obs[4 * q + 2], obs[4 * q + 3]);
             }
-            float* dst = obs_s + (lane >> 3) * OBS_S + (lane & 7);
+            float* dst = obs_s + (lane / TL) * OBS_S + (lane % TL);
 #pragma unroll
-            for (int i = 0; i < O; ++i) dst[i * TILE] = obs[i];
+            for (int i = 0; i < O; ++i) dst[i * TL] = obs[i];
         }
         __syncwarp();
 
         // ---- actor + critic forward for the warp's SUB tiles ----
 #pragma unroll
         for (int sub = 0; sub < SUB; ++sub) {
-            float h2[TILE][UPL];
-            mlp_forward_tile<O, A>(sw, obs_s + sub * OBS_S, h1_s, out_s + sub * OUT_S, lane, h2);
+            float h2[TL][UPL];
+            mlp_forward_tile<O, A, TL>(sw, obs_s + sub * OBS_S, h1_s, out_s + sub * TL * OUT_W, lane, h2);
         }
 
         // ---- per-env tail: value store, sample, env step ----
@@ -95,30 +95,42 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(drl_env_t env, c
     if (own) env_store(e, env, n);
 }
 
-template <int KIND, int SUB>
+template <int KIND, int SUB, int TL>
 int launch_rollout(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
                    const drl_ep_log_t& log, cudaStream_t st) {
     using S = EnvSpec<KIND>;
     constexpr int WS = SUB * OBS_S + H1_S + SUB * OUT_S;
+    (void)TL;
     const size_t smem = sizeof(float) * (Packed<S::O, S::A>::FWD + 4 + RO_WARPS * WS);
-    DRL_CUDA(cudaFuncSetAttribute(rollout_kernel<KIND, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int epc = TILE * SUB * RO_WARPS;
+    DRL_CUDA(cudaFuncSetAttribute(rollout_kernel<KIND, SUB, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int epc = TL * SUB * RO_WARPS;
     const int blocks = (env.num_envs + epc - 1) / epc;
-    rollout_kernel<KIND, SUB><<<blocks, RO_WARPS * 32, smem, st>>>(env, packed, T, step0, buf, log);
+    rollout_kernel<KIND, SUB, TL><<<blocks, RO_WARPS * 32, smem, st>>>(env, packed, T, step0, buf, log);
     DRL_LAUNCH_CHECK("rollout_kernel");
     return DRL_OK;
 }
 
-// envs per warp: small N wants as many warps as possible (latency-bound), large N amortises the
-// 8-lane env/sampling tail over more tiles.
-int pick_sub(int N) {
-    const char* ov = getenv("DRL_ROLLOUT_SUB");
-    if (ov) { int v = atoi(ov); if (v == 1 || v == 2 || v == 4) return v; }
-    const int warps_at_1 = (N + TILE - 1) / TILE;
+// envs per warp: small N wants as many warps as possible (the kernel is latency-bound at one warp per
+// scheduler), large N amortises the per-env tail (sampling, fp64 env step) over more tiles.
+// Returns envs per warp: 4 (one 4-env tile), 8, 16 or 32 (1, 2 or 4 8-env tiles).
+int pick_envs_per_warp(int N) {
+    const char* ov = getenv("DRL_ROLLOUT_EPW");
+    if (ov) { int v = atoi(ov); if (v == 4 || v == 8 || v == 16 || v == 32) return v; }
     const int sms = sm_count();
-    if (warps_at_1 <= sms * 24) return 1;
-    if (warps_at_1 <= sms * 48) return 2;
-    return 4;
+    if (N <= sms * 8 * 4) return 4;              // <= 8 warps per SM even at 4 envs per warp
+    const int warps_at_8 = (N + 7) / 8;
+    if (warps_at_8 <= sms * 24) return 8;
+    if (warps_at_8 <= sms * 48) return 16;
+    return 32;
+}
+
+template <int KIND>
+int dispatch_rollout(int epw, const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
+                     const drl_ep_log_t& l, cudaStream_t st) {
+    if (epw == 4) return launch_rollout<KIND, 1, 4>(env, packed, T, step0, buf, l, st);
+    if (epw == 8) return launch_rollout<KIND, 1, 8>(env, packed, T, step0, buf, l, st);
+    if (epw == 16) return launch_rollout<KIND, 2, 8>(env, packed, T, step0, buf, l, st);
+    return launch_rollout<KIND, 4, 8>(env, packed, T, step0, buf, l, st);
 }
 
 }  // namespace drl
@@ -137,14 +149,8 @@ extern "C" int drl_rollout(const drl_env_t* env, const drl_net_t* net, const flo
     DRL_REQUIRE(net->obs_dim == drl_env_obs_dim(env->kind) && net->num_actions == drl_env_num_actions(env->kind),
                 "drl_rollout: net shape does not match env kind %d", env->kind);
     const drl_ep_log_t l = log_or_empty(log);
-    const int sub = pick_sub(env->num_envs);
+    const int epw = pick_envs_per_warp(env->num_envs);
     cudaStream_t st = as_stream(stream);
-    if (env->kind == DRL_ENV_CARTPOLE) {
-        if (sub == 1) return launch_rollout<DRL_ENV_CARTPOLE, 1>(*env, packed, T, step0, *buf, l, st);
-        if (sub == 2) return launch_rollout<DRL_ENV_CARTPOLE, 2>(*env, packed, T, step0, *buf, l, st);
-        return launch_rollout<DRL_ENV_CARTPOLE, 4>(*env, packed, T, step0, *buf, l, st);
-    }
-    if (sub == 1) return launch_rollout<DRL_ENV_ACROBOT, 1>(*env, packed, T, step0, *buf, l, st);
-    if (sub == 2) return launch_rollout<DRL_ENV_ACROBOT, 2>(*env, packed, T, step0, *buf, l, st);
-    return launch_rollout<DRL_ENV_ACROBOT, 4>(*env, packed, T, step0, *buf, l, st);
+    if (env->kind == DRL_ENV_CARTPOLE) return dispatch_rollout<DRL_ENV_CARTPOLE>(epw, *env, packed, T, step0, *buf, l, st);
+    return dispatch_rollout<DRL_ENV_ACROBOT>(epw, *env, packed, T, step0, *buf, l, st);
 }

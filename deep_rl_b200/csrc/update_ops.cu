@@ -497,6 +497,7 @@ int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const floa
     g.grad_part = reinterpret_cast<float*>((char*)workspace + w.grad_partials);
     g.loss_part = reinterpret_cast<float*>((char*)workspace + w.loss_partials);
     g.ppad = w.ppad;
+    g.dbg = getenv("DRL_TC_DEBUG") ? reinterpret_cast<long long*>((char*)workspace + w.debug) : nullptr;
     if (flags & DRL_GRAD_TENSOR_CORES) return launch_grad_tc(net, g, P, grad_out, loss_terms_out, as_stream(stream));
     if (net->obs_dim == 4) return launch_grad<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, as_stream(stream));
     return launch_grad<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, as_stream(stream));

@@ -64,6 +64,9 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+// diagnostics: cycle stamps of CTA 0 (slot = tile * 16 + event), enabled with DRL_TC_DEBUG=1
+#define TC_STAMP(ev) do { if (g.dbg != nullptr && blockIdx.x == 0 && lane == 0 && k < 12) g.dbg[(warp == 0 ? 0 : 256) + k * 16 + (ev)] = clock64(); } while (0)
+
 enum : uint32_t { BAR_FWD = 1, BAR_BWD = 2, BAR_W1 = 3, BAR_PAIR0 = 4 };   // named barriers (0 = __syncthreads)
 
 template <int OW>
@@ -185,13 +188,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         };
         named_bar_sync(BAR_FWD, TC_THREADS);
         umma::fence_after_sync();
-        if (lane == 0) issue_fwd(0);
+        if (umma::elect_one()) issue_fwd(0);
         __syncwarp();
         for (uint32_t k = 0; k < nmy; ++k) {
             const uint32_t par = k & 1u, acc = k > 0 ? 1u : 0u;
             named_bar_sync(BAR_BWD, TC_THREADS);
             umma::fence_after_sync();
-            if (lane == 0) {
+            TC_STAMP(0);
+            if (umma::elect_one()) {
                 const uint32_t h1b = aH1 + par * 32768, obsb = aOBS + par * 4096;
 #pragma unroll
                 for (int n2 = 0; n2 < 2; ++n2)
@@ -214,15 +218,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                 umma::commit(bars + 2);
             }
             __syncwarp();
+            TC_STAMP(1);
             if (k + 1 < nmy) {
                 named_bar_sync(BAR_FWD, TC_THREADS);
                 umma::fence_after_sync();
-                if (lane == 0) issue_fwd(k + 1);
+                TC_STAMP(2);
+                if (umma::elect_one()) issue_fwd(k + 1);
                 __syncwarp();
+                TC_STAMP(3);
             }
             named_bar_sync(BAR_W1, TC_THREADS);
             umma::fence_after_sync();
-            if (lane == 0) {
+            TC_STAMP(4);
+            if (umma::elect_one()) {
 #pragma unroll
                 for (int kb = 0; kb < 8; ++kb)
                     umma::mma(tmem + C_W1, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
@@ -230,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                 umma::commit(bars + 3);
             }
             __syncwarp();
+            TC_STAMP(5);
         }
         umma::fence_before_sync();
         __syncthreads();           // epilogue barrier of the compute warps
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
 
     // =========================== compute warps ===========================
     const uint32_t trow = tmem + ((uint32_t)(rw * 32) << 16);   // this thread's TMEM lane
-    const float adv_mean = g.adv_stats[0], adv_std = g.adv_stats[1];
+    const float adv_mean = g.adv_stats[0], adv_rstd = 1.0f / (g.adv_stats[1] + 1e-8f);
     const float inv_m = 1.0f / (float)g.mb_count;
     const int wrow0 = net == 0 ? 0 : A;          // first head row of this net in sW4 / sB4
     const int nheads = net == 0 ? A : 1;
@@ -293,8 +302,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         const uint32_t par = k & 1u;
 
         // ================= X(k): heads, loss, output gradients, dz2 =================
+        TC_STAMP(0);
         mbar_wait(bars + 1, par);
         umma::fence_after_sync();
+        TC_STAMP(1);
         {
             float h[HU];
             umma::ld32(trow + C_ZF + net * 64 + u0, h);
@@ -329,7 +340,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                     xch[((net * 2 + half) * 4 + a) * TC_TILE + r] = ps[a];
                 }
             }
+            TC_STAMP(2);
             named_bar_sync(BAR_PAIR0 + net * 4 + rw, 64);
+            TC_STAMP(3);
             float out[A];
 #pragma unroll
             for (int a = 0; a < A; ++a) {
@@ -350,20 +363,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                     for (int a = 1; a < A; ++a) m = fmaxf(m, out[a]);
                     float se = 0.f;
 #pragma unroll
-                    for (int a = 0; a < A; ++a) se += expf(out[a] - m);
-                    const float lse = m + logf(se);
+                    for (int a = 0; a < A; ++a) se += __expf(out[a] - m);
+                    const float lse = m + __logf(se);
                     float lp[A], p[A];
                     float ent = 0.f, new_logp = 0.f;
 #pragma unroll
                     for (int a = 0; a < A; ++a) {
                         lp[a] = out[a] - lse;
-                        p[a] = expf(lp[a]);
+                        p[a] = __expf(lp[a]);
                         ent -= p[a] * lp[a];
                         if (a == rec_cur.act) new_logp = lp[a];
                     }
-                    const float nadv = (rec_cur.adv - adv_mean) / (adv_std + 1e-8f);
+                    const float nadv = (rec_cur.adv - adv_mean) * adv_rstd;
                     const float logratio = new_logp - rec_cur.logp_old;
-                    const float ratio = expf(logratio);
+                    const float ratio = __expf(logratio);
                     const float pg1 = -nadv * ratio;
                     const float pg2 = -nadv * fminf(fmaxf(ratio, 1.0f - g.clip_coef), 1.0f + g.clip_coef);
                     const float dpg = pg1 >= pg2 ? pg1 : 0.0f;
@@ -419,12 +432,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) h[4 * k4 + j] = dh[j] * fmaf(-h[4 * k4 + j], h[4 * k4 + j], 1.0f);
             }
+            TC_STAMP(4);
             if (k > 0) mbar_wait(bars + 3, (k - 1) & 1u);   // w1(k-1) has finished reading tDZ and tOBS[(k+1)&1]
+            TC_STAMP(5);
             store_half_row_sw128(tDZ + net * 16384, r, half * 4, h);
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
         named_bar_arrive(BAR_BWD, TC_THREADS);
+        TC_STAMP(6);
 
         // ================= Y(k): layer 1 of the next tile, hand fwd(k+1) (hides bwd(k)) =================
         if (k + 1 < nmy) {
@@ -435,8 +451,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         }
 
         // ================= Z(k): dz1 = dh1 * (1 - h1^2) (hides fwd(k+1)) =================
+        TC_STAMP(7);
         mbar_wait(bars + 2, par);
         umma::fence_after_sync();
+        TC_STAMP(8);
         {
             float dh[HU];
             umma::ld32(trow + C_DH + net * 64 + u0, dh);
@@ -460,6 +478,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         umma::fence_proxy_async();
         umma::fence_before_sync();
         named_bar_arrive(BAR_W1, TC_THREADS);
+        TC_STAMP(9);
     }
     mbar_wait(bars + 3, (nmy - 1) & 1u);
     umma::fence_after_sync();

@@ -1,0 +1,30 @@
+"""Cycle-stamp timeline of ppo_grad_tc_kernel (CTA 0), DRL_TC_DEBUG=1.  Usage: DRL_TC_DEBUG=1 python profiles/tc_stamps.py"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["DRL_TC_DEBUG"] = "1"
+import deep_rl_b200 as drl  # noqa: E402
+from deep_rl_b200 import _lib as L  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+cfg = drl.PPOConfig(num_envs=N, num_steps=128, total_timesteps=N * 128 * 8)
+tr = drl.PPOTrainer(cfg)
+for _ in range(3):
+    tr.update()
+torch.cuda.synchronize()
+ws = tr.workspace.cpu().numpy()
+dbg = ws[-4096:].view(np.int64)
+comp, mma = dbg[:256].reshape(16, 16), dbg[256:].reshape(16, 16)
+t0 = comp[1, 0]
+names_c = ["X start", "fwd ready", "heads done", "pair synced", "dz2 ready", "w1(k-1) ok", "BWD handed", "Z start(Y done)", "bwd ready", "W1 handed"]
+names_m = ["BWD sync", "bwd issued", "FWD sync", "fwd issued", "W1 sync", "w1 issued"]
+for k in range(1, 6):
+    print(f"--- tile {k} (cycles relative to X start of tile 1)")
+    ev = [(int(comp[k, i] - t0), "C " + names_c[i]) for i in range(10)] + [(int(mma[k, i] - t0), "M " + names_m[i]) for i in range(6)]
+    for t, n in sorted(ev):
+        print(f"{t:8d}  {n}")

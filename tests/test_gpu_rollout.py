@@ -19,7 +19,7 @@ def _check_rollout(env_id, N, T, seed, sub=None, rounds=2):
          auto-resets (Philox reset draws) and the episode log included."""
     import deep_rl_b200 as drl
     if sub is not None:
-        os.environ["DRL_ROLLOUT_SUB"] = str(sub)
+        os.environ["DRL_ROLLOUT_EPW"] = str(sub)
     try:
         cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=seed)
         tr = drl.PPOTrainer(cfg)
@@ -66,17 +66,20 @@ def _check_rollout(env_id, N, T, seed, sub=None, rounds=2):
         assert mism <= 1
         return tr
     finally:
-        os.environ.pop("DRL_ROLLOUT_SUB", None)
+        os.environ.pop("DRL_ROLLOUT_EPW", None)
 
 
 @pytest.mark.parametrize("env_id,N,T,sub", [
     ("CartPole-v1", 1, 128, None),        # the reference's own shape
     ("CartPole-v1", 13, 40, None),        # ragged: not a multiple of the 8-env tile
     ("CartPole-v1", 256, 64, None),
-    ("CartPole-v1", 100, 48, 2),
-    ("CartPole-v1", 300, 32, 4),
+    ("CartPole-v1", 100, 48, 16),         # envs per warp forced: 2 x 8-env tiles
+    ("CartPole-v1", 300, 32, 32),         # 4 x 8-env tiles
+    ("CartPole-v1", 77, 32, 8),
+    ("CartPole-v1", 4096, 16, None),      # C2 width: picks the 4-env tile
     ("Acrobot-v1", 40, 48, None),
-    ("Acrobot-v1", 70, 24, 4),
+    ("Acrobot-v1", 70, 24, 32),
+    ("Acrobot-v1", 50, 24, 8),
 ])
 def test_rollout_vs_oracle(env_id, N, T, sub):
     _check_rollout(env_id, N, T, seed=3, sub=sub)
