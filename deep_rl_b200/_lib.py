@@ -58,7 +58,7 @@ SIGNATURES = {
     "drl_policy_forward": (C.c_int, [C.POINTER(NetT), f32p, f32p, C.c_int64, f32p, f32p, C.c_void_p]),
     "drl_sample": (C.c_int, [f32p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint64, i32p, f32p, C.c_void_p]),
     "drl_rollout": (C.c_int, [C.POINTER(EnvT), C.POINTER(NetT), f32p, C.c_int32, C.c_uint64, C.POINTER(RolloutBufT),
-                              C.POINTER(EpLogT), C.c_void_p]),
+                              C.POINTER(EpLogT), C.c_uint32, C.c_void_p]),
     "drl_gae": (C.c_int, [C.POINTER(RolloutBufT), C.POINTER(NetT), C.c_int32, C.c_int32, C.c_float, C.c_float, f32p,
                           f32p, f32p, C.c_void_p]),
     "drl_permutation": (C.c_int, [u32p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),

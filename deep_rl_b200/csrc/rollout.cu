@@ -13,6 +13,8 @@ namespace drl {
 
 int check_env(const drl_env_t* env);
 drl_ep_log_t log_or_empty(const drl_ep_log_t* log);
+int launch_rollout_tc(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
+                      const drl_ep_log_t& log, cudaStream_t st);   // rollout_tc.cu
 
 constexpr int RO_WARPS = 4;
 
@@ -138,7 +140,7 @@ int dispatch_rollout(int epw, const drl_env_t& env, const float* packed, int T, 
 using namespace drl;
 
 extern "C" int drl_rollout(const drl_env_t* env, const drl_net_t* net, const float* packed, int32_t T, uint64_t step0,
-                           const drl_rollout_buf_t* buf, const drl_ep_log_t* log, void* stream) {
+                           const drl_rollout_buf_t* buf, const drl_ep_log_t* log, uint32_t flags, void* stream) {
     int rc = check_env(env);
     if (rc != DRL_OK) return rc;
     rc = check_net(net);
@@ -149,8 +151,9 @@ extern "C" int drl_rollout(const drl_env_t* env, const drl_net_t* net, const flo
     DRL_REQUIRE(net->obs_dim == drl_env_obs_dim(env->kind) && net->num_actions == drl_env_num_actions(env->kind),
                 "drl_rollout: net shape does not match env kind %d", env->kind);
     const drl_ep_log_t l = log_or_empty(log);
-    const int epw = pick_envs_per_warp(env->num_envs);
     cudaStream_t st = as_stream(stream);
+    if (flags & DRL_ROLLOUT_TENSOR_CORES) return launch_rollout_tc(*env, packed, T, step0, *buf, l, st);
+    const int epw = pick_envs_per_warp(env->num_envs);
     if (env->kind == DRL_ENV_CARTPOLE) return dispatch_rollout<DRL_ENV_CARTPOLE>(epw, *env, packed, T, step0, *buf, l, st);
     return dispatch_rollout<DRL_ENV_ACROBOT>(epw, *env, packed, T, step0, *buf, l, st);
 }

@@ -23,15 +23,11 @@
 // z2 and dh1 have separate TMEM columns, records are prefetched one tile ahead and their indices two tiles ahead.  All weight-gradient accumulators live in TMEM for the whole kernel (432 of 512 columns used) and
 // are written once, as this CTA's partial gradient, at the end.
 #include "drl_pack.cuh"
-#include "drl_umma.cuh"
+#include "drl_tc_common.cuh"
 #include "drl_update.cuh"
 
 namespace drl {
 
-constexpr int TC_COMPUTE = 512;           // 16 compute warps
-constexpr int TC_THREADS = TC_COMPUTE + 32;  // + the MMA-issuer warp
-constexpr int HU = 32;                     // hidden units per compute thread
-constexpr int TC_TILE = 128;
 // TMEM columns
 constexpr uint32_t C_ZF = 0, C_DH = 128, C_W2 = 256, C_B2 = 384, C_W4 = 400, C_W1 = 416, TC_COLS = 512;
 
@@ -51,19 +47,6 @@ struct TcSmem {
     static constexpr int TOTAL = OFF_RED + 16 * 12 * 4 + 1024;   // + alignment slack
 };
 
-// tanh on the SFU (one MUFU op, |abs err| ~ 5e-4): below the bf16 rounding the activations get anyway
-__device__ __forceinline__ float tanh_mufu(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t count) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
 // diagnostics: cycle stamps of CTA 0 (slot = tile * 16 + event), enabled with DRL_TC_DEBUG=1
 #define TC_STAMP(ev) do { if (g.dbg != nullptr && blockIdx.x == 0 && lane == 0 && k < 12) g.dbg[(warp == 0 ? 0 : 256) + k * 16 + (ev)] = clock64(); } while (0)
 
@@ -100,19 +83,6 @@ __device__ __forceinline__ void tc_load_record(TcRecord<OW>& rc, const GradArgs&
         }
         const float4 t4 = __ldg(r4 + RW / 4 - 1);
         rc.logp_old = t4.x; rc.adv = t4.y; rc.val_old = t4.z; rc.act = __float_as_int(t4.w);
-    }
-}
-
-// four 16-byte chunks (32 bf16) of row `row` of a SW128 tile, starting at chunk c0
-__device__ __forceinline__ void store_half_row_sw128(unsigned char* tile, int row, int c0, const float (&v)[HU]) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint4 q;
-        q.x = umma::pack_bf16(v[8 * c + 0], v[8 * c + 1]);
-        q.y = umma::pack_bf16(v[8 * c + 2], v[8 * c + 3]);
-        q.z = umma::pack_bf16(v[8 * c + 4], v[8 * c + 5]);
-        q.w = umma::pack_bf16(v[8 * c + 6], v[8 * c + 7]);
-        *reinterpret_cast<uint4*>(tile + umma::sw128_off(row, c0 + c)) = q;
     }
 }
 

@@ -49,6 +49,8 @@ class PPOConfig:
     hidden: int = 64
     num_minibatches: int = 4     # reference: minibatch_size = num_steps // 4
     anneal_lr: bool = True
+    rollout_precision: str = "auto"  # "bf16": tcgen05 rollout (128 envs per CTA); "fp32": CUDA-core rollout; "auto": bf16 when
+                                     # the update is bf16 and there are enough envs to fill the GPU with 128-env CTAs
     update_precision: str = "bf16"   # "bf16": tcgen05 tensor-core update (bf16 operands, fp32 accumulate); "fp32": CUDA-core update
 
     @property
@@ -134,6 +136,11 @@ class PPOTrainer:
         if cfg.update_precision not in ("bf16", "fp32"):
             raise ValueError(f"update_precision={cfg.update_precision!r}")
         self.grad_flags = 1 if cfg.update_precision == "bf16" else 0
+        if cfg.rollout_precision not in ("auto", "bf16", "fp32"):
+            raise ValueError(f"rollout_precision={cfg.rollout_precision!r}")
+        tc_rollout = cfg.rollout_precision == "bf16" or (cfg.rollout_precision == "auto" and cfg.update_precision == "bf16"
+                                                         and N >= 128 * 128)
+        self.rollout_flags = 1 if tc_rollout else 0
         self.adam_step = 0
         self.update_idx = 0
         self.global_step = 0       # env steps taken on this rank's envs x world (reference counter at N=1)
@@ -163,7 +170,7 @@ class PPOTrainer:
         with _Phase(self, "rollout"):
             _lib.check(self.L.drl_rollout(C.byref(self.env.struct), C.byref(self.net), self.agent.packed.data_ptr(),
                                           cfg.num_steps, self.env.step_count, C.byref(self.buf),
-                                          C.byref(self.env.log.struct), _lib.stream_ptr()))
+                                          C.byref(self.env.log.struct), self.rollout_flags, _lib.stream_ptr()))
         self.env.step_count += cfg.num_steps
         self.global_step += cfg.num_steps * cfg.num_envs * self.world
         self.kernel_launches += 1

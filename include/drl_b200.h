@@ -114,8 +114,9 @@ int drl_sample(const float* logits /*[n][A]*/, int64_t n, int32_t num_actions, u
                uint64_t step, int32_t* act_out /*[n]*/, float* logp_out /*[n]*/, void* stream);
 
 /* ---- fused rollout, ppo.py:110-141: T x (actor+critic forward, sample, env step, stores) ---- */
+#define DRL_ROLLOUT_TENSOR_CORES 1u   /* flags: hidden layers on tcgen05 (bf16 operands, fp32 accumulate), 128 envs per CTA */
 int drl_rollout(const drl_env_t* env, const drl_net_t* net, const float* packed, int32_t T, uint64_t step0,
-                const drl_rollout_buf_t* buf, const drl_ep_log_t* log, void* stream);
+                const drl_rollout_buf_t* buf, const drl_ep_log_t* log, uint32_t flags, void* stream);
 
 /* ---- GAE + returns, ppo.py:144-151; optionally packs per-sample records for the update ----
  * adv_out/ret_out are [T+1][N] (row T = 0 / val[T], as the reference leaves them).

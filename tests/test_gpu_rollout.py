@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 from oracle import clib, ppo_oracle as po  # noqa: E402
 
 
-def _check_rollout(env_id, N, T, seed, sub=None, rounds=2):
+def _check_rollout(env_id, N, T, seed, sub=None, rounds=2, tc=False):
     """Teacher-forced check of drl_rollout against the oracle:
        * oracle forward on the kernel's stored obs[t] must reproduce val[t] and the log-prob,
        * the oracle sampler fed the oracle logits must pick the kernel's action (bit-exact unless the
@@ -21,8 +21,11 @@ def _check_rollout(env_id, N, T, seed, sub=None, rounds=2):
     if sub is not None:
         os.environ["DRL_ROLLOUT_EPW"] = str(sub)
     try:
-        cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=seed)
+        cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=seed, rollout_precision="bf16" if tc else "fp32")
         tr = drl.PPOTrainer(cfg)
+        # tensor-core rollout: bf16 GEMM operands + SFU tanh => logits within ~1e-2 of the fp32 oracle
+        tol = 3e-2 if tc else 2e-5
+        edge = 3e-2 if tc else 2e-6
         O, A = tr.env.obs_dim, tr.env.num_actions
         ora = clib.OracleVecEnv(env_id, N, seed=seed)
         obs0 = ora.reset()
@@ -40,19 +43,25 @@ def _check_rollout(env_id, N, T, seed, sub=None, rounds=2):
             for t in range(T + 1):
                 with torch.no_grad():
                     logits, v = po.mlp_forward(flat, torch.from_numpy(np.ascontiguousarray(obs[t])), O, 64, A)
-                np.testing.assert_allclose(val[t], v.numpy(), rtol=0, atol=2e-5, err_msg=f"value t={t}")
+                np.testing.assert_allclose(val[t], v.numpy(), rtol=0, atol=tol, err_msg=f"value t={t}")
                 if t == T:
                     break
                 step = ora.step_count
                 wa, _ = clib.sample(logits.numpy(), seed, 0, step)
                 lsm = torch.log_softmax(logits, -1).numpy()
-                np.testing.assert_allclose(logp[t], lsm[np.arange(N), act[t]], rtol=0, atol=2e-5, err_msg=f"logp t={t}")
+                np.testing.assert_allclose(logp[t], lsm[np.arange(N), act[t]], rtol=0, atol=tol, err_msg=f"logp t={t}")
                 bad = np.nonzero(wa != act[t])[0]
                 for i in bad:   # only allowed within rounding distance of a CDF edge
                     u = clib.action_uniform(seed, int(i), step)
                     cdf = np.cumsum(np.exp(lsm[i].astype(np.float64)))
-                    assert np.min(np.abs(cdf[:-1] - u)) < 2e-6, f"action mismatch env {i} t={t}: u={u} cdf={cdf}"
+                    assert np.min(np.abs(cdf[:-1] - u)) < edge, f"action mismatch env {i} t={t}: u={u} cdf={cdf}"
                     mism += 1
+                if A == 2:   # self-consistency with the kernel's own probabilities: a == 0 iff u < p0
+                    pa = np.exp(logp[t].astype(np.float64))
+                    p0 = np.where(act[t] == 0, pa, 1.0 - pa)
+                    us = np.array([clib.action_uniform(seed, int(i), step) for i in range(N)])
+                    wrong = ((us < p0) != (act[t] == 0)) & (np.abs(us - p0) > 1e-5)
+                    assert not wrong.any(), f"sampler inconsistent with stored log-prob at t={t}: envs {np.nonzero(wrong)[0]}"
                 o, r, d, info = ora.step(act[t])
                 np.testing.assert_allclose(obs[t + 1], o, rtol=0, atol=1e-6, err_msg=f"obs t={t + 1}")
                 assert np.array_equal(rew[t + 1], r) and np.array_equal(done[t + 1], d), f"rew/done t={t + 1}"
@@ -63,7 +72,7 @@ def _check_rollout(env_id, N, T, seed, sub=None, rounds=2):
             assert cnt == len(fin)
             assert entries == sorted(fin)
             np.testing.assert_allclose(tr.env.get_state().cpu().numpy(), ora.state, rtol=0, atol=1e-9)
-        assert mism <= 1
+        assert mism <= (max(2, int(0.02 * N * T * rounds)) if tc else 1)
         return tr
     finally:
         os.environ.pop("DRL_ROLLOUT_EPW", None)
@@ -83,6 +92,11 @@ def _check_rollout(env_id, N, T, seed, sub=None, rounds=2):
 ])
 def test_rollout_vs_oracle(env_id, N, T, sub):
     _check_rollout(env_id, N, T, seed=3, sub=sub)
+
+
+@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 300, 24), ("CartPole-v1", 128, 40), ("CartPole-v1", 1, 16), ("Acrobot-v1", 130, 16)])
+def test_tensor_core_rollout_vs_oracle(env_id, N, T):
+    _check_rollout(env_id, N, T, seed=3, tc=True)
 
 
 def test_rollout_world_size_invariance():
