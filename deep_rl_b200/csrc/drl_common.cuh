@@ -85,7 +85,10 @@ struct Packed {
     static constexpr int TC_B2 = TC_B1 + 2 * H;
     static constexpr int TC_W4 = TC_B2 + 2 * H;
     static constexpr int TC_B4 = TC_W4 + (A + 1) * H;
-    static constexpr int TC_END = TC_B4 + 4;
+    //   TC_W1B: bf16 [2][2 chunks][H rows][8]: K-major no-swizzle B operand of the layer-1 GEMM, K = 16:
+    //           k < O: W1[n][k], k == O: b1[n], k in [8, 8+O): W1[n][k-8] again (multiplies the low half of obs)
+    static constexpr int TC_W1B = TC_B4 + 4;
+    static constexpr int TC_END = TC_W1B + 2 * 2 * H * 8 / 2;
     static constexpr int TOTAL = TC_END;
     // canonical (state_dict) layout
     static constexpr int C_NET = H * O + H + H * H + H;          // trunk params per net

@@ -20,12 +20,16 @@ __device__ __forceinline__ void packed_store(float* __restrict__ packed, int i, 
         const int o = r / O, k = r % O;
         packed[P::W1T + (net * O + k) * H + perm_pos(o)] = v;
         packed[P::TC_W1 + (net * H + o) * P::OW + k] = v;
+        __nv_bfloat16* w1b = reinterpret_cast<__nv_bfloat16*>(packed + P::TC_W1B) + net * (2 * H * 8);
+        w1b[o * 8 + k] = __float2bfloat16_rn(v);             // chunk 0, k < O  (x_hi)
+        w1b[H * 8 + o * 8 + k] = __float2bfloat16_rn(v);     // chunk 1, k + 8  (x_lo)
         return;
     }
     r -= H * O;
     if (r < H) {
         packed[P::B1 + net * H + perm_pos(r)] = v;
         packed[P::TC_B1 + net * H + r] = v;
+        reinterpret_cast<__nv_bfloat16*>(packed + P::TC_W1B)[net * (2 * H * 8) + r * 8 + O] = __float2bfloat16_rn(v);   // ones column
         return;
     }
     r -= H;
@@ -61,7 +65,7 @@ __device__ __forceinline__ void packed_store(float* __restrict__ packed, int i, 
 // ---- update workspace (caller-owned, zero-initialised once) ----
 constexpr int MAX_GRAD_CTAS = 160;   // >= SM count (148); the grad kernel runs one persistent CTA per SM
 constexpr int MAX_MINIBATCHES = 16;
-constexpr int STAT_PARTS = 64;       // partial-sum CTAs per minibatch in drl_adv_stats
+constexpr int STAT_PARTS = 512;      // max partial-sum CTAs per minibatch in drl_adv_stats
 constexpr int LOSS_TERMS = 8;
 
 struct WorkspaceLayout {

@@ -56,21 +56,25 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Permutation: idx[i] = cycle-walked alternating Feistel network keyed by Philox.
-// Integer-only => bit-exact with the CPU oracle's restatement.
+// Permutation: idx[i] = cycle-walked 6-round alternating Feistel network on ceil(log2 B) bits.  Round keys are
+// Philox words (seed; epoch_ctr, rank), round function = murmur3 finalizer of (half ^ key).
+// Integer-only => bit-exact with the CPU oracle's restatement.  HBM-bound: 4 bytes written per index.
 // ---------------------------------------------------------------------------------------------
 constexpr int PERM_ROUNDS = 6;
 
-__device__ __forceinline__ uint32_t perm_index(uint32_t i, uint32_t B, uint32_t a, uint32_t b, uint64_t seed,
-                                               uint32_t epoch_ctr, uint32_t rank) {
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+__device__ __forceinline__ uint32_t perm_index(uint32_t i, uint32_t B, uint32_t a, uint32_t b, const uint32_t (&keys)[8]) {
     uint32_t x = i;
     do {
         uint32_t lb = a, rb = b;
         uint32_t L = x >> rb, R = x & ((1u << rb) - 1u);
 #pragma unroll
         for (uint32_t r = 0; r < PERM_ROUNDS; ++r) {
-            const uint4 o = philox_seeded(seed, R, epoch_ctr, r | (rank << 8), TAG_PERM);
-            const uint32_t nR = L ^ (o.x & ((1u << lb) - 1u));
+            const uint32_t nR = L ^ (fmix32(R ^ keys[r]) & ((1u << lb) - 1u));
             L = R;
             R = nR;
             const uint32_t t = lb; lb = rb; rb = t;
@@ -82,9 +86,12 @@ __device__ __forceinline__ uint32_t perm_index(uint32_t i, uint32_t B, uint32_t 
 
 __global__ void __launch_bounds__(256) permutation_kernel(uint32_t* __restrict__ idx, uint32_t B, uint32_t a, uint32_t b,
                                                            uint64_t seed, uint32_t epoch_ctr, uint32_t rank) {
+    const uint4 k0 = philox_seeded(seed, epoch_ctr, rank, 0u, TAG_PERM);
+    const uint4 k1 = philox_seeded(seed, epoch_ctr, rank, 1u, TAG_PERM);
+    const uint32_t keys[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride)
-        idx[i] = perm_index(i, B, a, b, seed, epoch_ctr, rank);
+        idx[i] = perm_index(i, B, a, b, keys);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -96,11 +103,24 @@ template <int RW>
 __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ rec, const uint32_t* __restrict__ idx,
                                                          uint32_t B, uint32_t mb_size, float* __restrict__ stats_out,
                                                          double* __restrict__ partials, uint32_t* __restrict__ counter) {
-    const uint32_t mb = blockIdx.y, part = blockIdx.x, nmb = gridDim.y;
+    const uint32_t mb = blockIdx.y, part = blockIdx.x, nmb = gridDim.y, nparts = gridDim.x;
     const uint32_t lo = mb * mb_size;
     const uint32_t hi = min(B, lo + mb_size);
     double s = 0.0, ss = 0.0;
-    for (uint32_t i = lo + part * blockDim.x + threadIdx.x; i < hi; i += STAT_PARTS * blockDim.x) {
+    // four independent (index -> record) gathers in flight per thread: the loop is latency-bound otherwise
+    const uint32_t step = nparts * 256u;
+    uint32_t i = lo + part * 256u + threadIdx.x;
+    for (; i + 3u * step < hi; i += 4u * step) {
+        uint32_t sx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sx[j] = idx ? __ldg(idx + i + j * step) : i + j * step;
+        float av[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) av[j] = __ldg(rec + (size_t)sx[j] * RW + (RW - 3));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double a = (double)av[j]; s += a; ss = fma(a, a, ss); }
+    }
+    for (; i < hi; i += step) {
         const uint32_t sidx = idx ? idx[i] : i;
         const double a = (double)rec[(size_t)sidx * RW + (RW - 3)];
         s += a;
@@ -120,14 +140,14 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict_
         partials[((size_t)mb * STAT_PARTS + part) * 2 + 1] = tss;
         __threadfence();
         const uint32_t done = atomicAdd(counter, 1u);
-        is_last = (done == nmb * STAT_PARTS - 1);
+        is_last = (done == nmb * nparts - 1);
     }
     __syncthreads();
     if (is_last && threadIdx.x < nmb) {
         __threadfence();
         const uint32_t k = threadIdx.x;
         double ts = 0.0, tss = 0.0;
-        for (int p = 0; p < STAT_PARTS; ++p) {
+        for (uint32_t p = 0; p < nparts; ++p) {
             ts += __ldcg(&partials[((size_t)k * STAT_PARTS + p) * 2 + 0]);
             tss += __ldcg(&partials[((size_t)k * STAT_PARTS + p) * 2 + 1]);
         }
@@ -173,7 +193,7 @@ int drl_permutation(uint32_t* idx_out, uint32_t B, uint64_t seed, uint32_t epoch
     uint32_t k = 2;
     while (k < 32 && (1ull << k) < (unsigned long long)B) ++k;
     const uint32_t a = k / 2, b = k - a;
-    long long blocks = ((long long)B + 255) / 256;
+    long long blocks = ((long long)B + 2047) / 2048;          // ~8 indices per thread amortise the two Philox blocks
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     permutation_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(idx_out, B, a, b, seed, epoch_ctr, rank);
@@ -193,7 +213,10 @@ int drl_adv_stats(const drl_net_t* net, const float* rec, const uint32_t* idx, u
     DRL_REQUIRE(workspace_bytes >= w.total, "drl_adv_stats: workspace %zu < %zu bytes", workspace_bytes, w.total);
     uint32_t* counter = reinterpret_cast<uint32_t*>((char*)workspace + w.counters);
     double* partials = reinterpret_cast<double*>((char*)workspace + w.stat_partials);
-    dim3 grid(STAT_PARTS, nmb);
+    uint32_t nparts = (mb_size + 4095u) / 4096u;               // >= 16 gathers per thread, up to STAT_PARTS CTAs per minibatch
+    if (nparts > (uint32_t)STAT_PARTS) nparts = STAT_PARTS;
+    if (nparts == 0) nparts = 1;
+    dim3 grid(nparts, nmb);
     if (net->obs_dim <= 4) adv_stats_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(rec, idx, B, mb_size, stats_out, partials, counter);
     else adv_stats_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(rec, idx, B, mb_size, stats_out, partials, counter);
     DRL_LAUNCH_CHECK("adv_stats_kernel");

@@ -39,9 +39,9 @@ struct TcSmem {
     static constexpr int OFF_H1 = (OFF_W + W_BYTES + 1023) / 1024 * 1024;   // two buffers x (actor, critic) x 16 KB
     static constexpr int OFF_H2 = OFF_H1 + 65536;
     static constexpr int OFF_DZ = OFF_H2 + 32768;
-    static constexpr int OFF_OBS = OFF_DZ + 32768;     // two NS16 buffers (tile parity)
-    static constexpr int OFF_DOUT = OFF_OBS + 8192;    // one NS16 buffer
-    static constexpr int OFF_BAR = OFF_DOUT + 4096;    // 4 mbarriers + TMEM slot
+    static constexpr int OFF_OBS = OFF_DZ + 32768;     // three NS16 buffers [obs_hi|1|obs_lo] (tile % 3)
+    static constexpr int OFF_DOUT = OFF_OBS + 12288;   // one NS16 buffer
+    static constexpr int OFF_BAR = OFF_DOUT + 4096;    // 5 mbarriers + TMEM slot
     static constexpr int OFF_XCH = OFF_BAR + 64;       // head partial sums [net][half][A][128 rows] fp32
     static constexpr int OFF_RED = OFF_XCH + 2 * 2 * 4 * 128 * 4;
     static constexpr int TOTAL = OFF_RED + 16 * 12 * 4 + 1024;   // + alignment slack
@@ -50,7 +50,7 @@ struct TcSmem {
 // diagnostics: cycle stamps of CTA 0 (slot = tile * 16 + event), enabled with DRL_TC_DEBUG=1
 #define TC_STAMP(ev) do { if (g.dbg != nullptr && blockIdx.x == 0 && lane == 0 && k < 12) g.dbg[(warp == 0 ? 0 : 256) + k * 16 + (ev)] = clock64(); } while (0)
 
-enum : uint32_t { BAR_FWD = 1, BAR_BWD = 2, BAR_W1 = 3, BAR_PAIR0 = 4 };   // named barriers (0 = __syncthreads)
+enum : uint32_t { BAR_FWD = 1, BAR_BWD = 2, BAR_W1 = 3, BAR_PAIR0 = 4, BAR_L1 = 12 };   // named barriers (0 = __syncthreads)
 
 template <int OW>
 struct TcRecord {       // one sample record, held in registers between its prefetch and its use
@@ -99,13 +99,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     const float* sB2 = sB1 + 2 * H;
     const float* sW4 = sB2 + 2 * H;
     const float* sB4 = sW4 + (A + 1) * H;
+    unsigned char* tW1B = reinterpret_cast<unsigned char*>(const_cast<float*>(sB4 + 4));   // bf16 layer-1 B tiles
     unsigned char* tH1 = sm + S::OFF_H1;
     unsigned char* tH2 = sm + S::OFF_H2;
     unsigned char* tDZ = sm + S::OFF_DZ;
     unsigned char* tOBS = sm + S::OFF_OBS;
     unsigned char* tDOUT = sm + S::OFF_DOUT;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd, 2 bwd, 3 w1
-    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd, 2 bwd, 3 w1, 4 layer 1
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 5);
     float* xch = reinterpret_cast<float*>(sm + S::OFF_XCH);
     float* red = reinterpret_cast<float*>(sm + S::OFF_RED);
 
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     // ---- prologue: barriers, TMEM, weights by TMA bulk copy ----
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
         mbar_fence_init();
     }
     if (warp == 1) umma::tmem_alloc(slot, TC_COLS);
@@ -145,7 +146,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         constexpr uint32_t ID_DH1 = umma::make_idesc(128, 64, false, true);
         constexpr uint32_t ID_W2 = umma::make_idesc(128, 128, true, true);
         constexpr uint32_t ID_N16 = umma::make_idesc(128, 16, true, true);
-        mbar_wait(bars, 0);   // W2 tiles have landed
+        mbar_wait(bars, 0);   // weight tiles have landed
+        const uint32_t aW1B = smem_u32(tW1B);
+        constexpr uint32_t ID_L1 = umma::make_idesc(128, 64, false, false);
+        // layer 1 of tile k: z1 = [obs_hi|1|obs_lo] . [W1|b1|W1]^T, K = 16, both operands K-major without swizzle
+        auto issue_l1 = [&](uint32_t k) {
+            const uint32_t obsb = aOBS + (k % 3u) * 4096;
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2)
+                umma::mma(tmem + C_ZF + n2 * 64, umma::make_desc(obsb, 2048, 128, umma::LAYOUT_NONE),
+                          umma::make_desc(aW1B + n2 * 2048, 1024, 128, umma::LAYOUT_NONE), ID_L1, 0u);
+            umma::commit(bars + 4);
+        };
         auto issue_fwd = [&](uint32_t k) {
             const uint32_t h1b = aH1 + (k & 1u) * 32768;
 #pragma unroll
@@ -156,17 +168,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                               umma::make_desc(aW2 + n2 * 8192 + kb * 32, 16, 1024, umma::LAYOUT_SW128), ID_FWD, kb > 0);
             umma::commit(bars + 1);
         };
+        named_bar_sync(BAR_L1, TC_THREADS);
+        umma::fence_after_sync();
+        if (umma::elect_one()) issue_l1(0);
+        __syncwarp();
         named_bar_sync(BAR_FWD, TC_THREADS);
         umma::fence_after_sync();
         if (umma::elect_one()) issue_fwd(0);
         __syncwarp();
         for (uint32_t k = 0; k < nmy; ++k) {
             const uint32_t par = k & 1u, acc = k > 0 ? 1u : 0u;
+            const uint32_t obsb = aOBS + (k % 3u) * 4096;
+            if (k + 1 < nmy) {
+                named_bar_sync(BAR_L1, TC_THREADS);      // z2(k) consumed, obs tile of k+1 written
+                umma::fence_after_sync();
+                if (umma::elect_one()) issue_l1(k + 1);
+                __syncwarp();
+            }
             named_bar_sync(BAR_BWD, TC_THREADS);
             umma::fence_after_sync();
             TC_STAMP(0);
             if (umma::elect_one()) {
-                const uint32_t h1b = aH1 + par * 32768, obsb = aOBS + par * 4096;
+                const uint32_t h1b = aH1 + par * 32768;
 #pragma unroll
                 for (int n2 = 0; n2 < 2; ++n2)
 #pragma unroll
@@ -204,7 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
 #pragma unroll
                 for (int kb = 0; kb < 8; ++kb)
                     umma::mma(tmem + C_W1, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
-                              umma::make_desc(aOBS + par * 4096 + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
+                              umma::make_desc(obsb + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
                 umma::commit(bars + 3);
             }
             __syncwarp();
@@ -229,42 +252,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     uint32_t s_next = tc_sample_index(g, blockIdx.x + gridDim.x, ntiles, r);
     mbar_wait(bars, 0);
 
-    // P0: layer 1 (this thread's 32 units) of tile k from record rc into buffer k & 1, then hand fwd(k)
-    auto phase0 = [&](const TcRecord<OW>& rc, uint32_t k) {
-        const uint32_t buf = k & 1u;
-        {
-            float h[HU];
-            const float* w1 = sW1 + (net * H + u0) * OW;
-            const float* b1 = sB1 + net * H + u0;
+    // owners (warps 0-3): row r of the [obs_hi | 1 | 0.. | obs_lo | 0..] tile of tile k -- A operand of the layer-1
+    // GEMM and B operand of the dW1/db1 and db2 GEMMs.  obs = hi + lo to 16 mantissa bits.
+    auto write_obs_tile = [&](const TcRecord<OW>& rc, uint32_t k) {
+        float o16[16];
 #pragma unroll
-            for (int k4 = 0; k4 < HU / 4; ++k4) {
-                const float4 bb = *reinterpret_cast<const float4*>(b1 + 4 * k4);
-                const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+        for (int i = 0; i < 16; ++i) o16[i] = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int kk = 4 * k4 + j;
-                    float z = bv[j];
-#pragma unroll
-                    for (int q = 0; q < OW / 4; ++q) {
-                        const float4 w = *reinterpret_cast<const float4*>(w1 + kk * OW + 4 * q);
-                        z = fmaf(rc.x[4 * q + 3], w.w, fmaf(rc.x[4 * q + 2], w.z, fmaf(rc.x[4 * q + 1], w.y, fmaf(rc.x[4 * q], w.x, z))));
-                    }
-                    h[kk] = tanh_mufu(z);
-                }
-            }
-            store_half_row_sw128(tH1 + buf * 32768 + net * 16384, r, half * 4, h);
+        for (int i = 0; i < O; ++i) {
+            const float hi = __bfloat162float(__float2bfloat16_rn(rc.x[i]));
+            o16[i] = hi;
+            o16[8 + i] = rc.x[i] - hi;
         }
-        if (warp < 4) {   // [obs | 1 | 0...] row of the NS16 tile (B operand of the dW1/db1 and db2 GEMMs)
-            float o16[16];
+        o16[O] = 1.0f;
+        umma::store_row_ns16(tOBS + (k % 3u) * 4096, TC_TILE, r, o16);
+    };
+    // layer-1 epilogue of tile k: z1 from TMEM -> tanh -> bf16 h1 tile (buffer k & 1), then hand fwd(k)
+    auto phase0 = [&](uint32_t k) {
+        mbar_wait(bars + 4, k & 1u);
+        umma::fence_after_sync();
+        float h[HU];
+        umma::ld32(trow + C_ZF + net * 64 + u0, h);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o16[i] = i < O ? rc.x[i < OW ? i : 0] : (i == O ? 1.0f : 0.0f);
-            umma::store_row_ns16(tOBS + buf * 4096, TC_TILE, r, o16);
-        }
+        for (int j = 0; j < HU; ++j) h[j] = tanh_mufu(h[j]);
+        store_half_row_sw128(tH1 + (k & 1u) * 32768 + net * 16384, r, half * 4, h);
         umma::fence_proxy_async();
+        umma::fence_before_sync();
         named_bar_arrive(BAR_FWD, TC_THREADS);
     };
 
-    phase0(rec_cur, 0);
+    if (warp < 4) write_obs_tile(rec_cur, 0);
+    umma::fence_proxy_async();
+    named_bar_arrive(BAR_L1, TC_THREADS);
+    phase0(0);
     tc_load_record<OW, OP, RW>(rec_next, g, s_next);
     s_next = tc_sample_index(g, blockIdx.x + 2 * gridDim.x, ntiles, r);
 
@@ -279,6 +299,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         {
             float h[HU];
             umma::ld32(trow + C_ZF + net * 64 + u0, h);
+            if (k + 1 < nmy) {   // z2(k) is in registers: the layer-1 GEMM of tile k+1 may overwrite its TMEM columns
+                if (warp < 4) write_obs_tile(rec_next, k + 1);
+                umma::fence_proxy_async();
+                umma::fence_before_sync();
+                named_bar_arrive(BAR_L1, TC_THREADS);
+            }
             const float* b2 = sB2 + net * H + u0;
 #pragma unroll
             for (int k4 = 0; k4 < HU / 4; ++k4) {
@@ -403,7 +429,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                 for (int j = 0; j < 4; ++j) h[4 * k4 + j] = dh[j] * fmaf(-h[4 * k4 + j], h[4 * k4 + j], 1.0f);
             }
             TC_STAMP(4);
-            if (k > 0) mbar_wait(bars + 3, (k - 1) & 1u);   // w1(k-1) has finished reading tDZ and tOBS[(k+1)&1]
+            if (k > 0) mbar_wait(bars + 3, (k - 1) & 1u);   // w1(k-1) has finished reading tDZ
             TC_STAMP(5);
             store_half_row_sw128(tDZ + net * 16384, r, half * 4, h);
         }
@@ -414,7 +440,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
 
         // ================= Y(k): layer 1 of the next tile, hand fwd(k+1) (hides bwd(k)) =================
         if (k + 1 < nmy) {
-            phase0(rec_next, k + 1);
+            phase0(k + 1);
             rec_cur = rec_next;
             tc_load_record<OW, OP, RW>(rec_next, g, s_next);
             s_next = tc_sample_index(g, blockIdx.x + (k + 3) * gridDim.x, ntiles, r);
@@ -463,7 +489,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         part[base + H * O + H + H * H + o] = v16[O];   // db2
         umma::ld16(trow + C_W1, v16);
 #pragma unroll
-        for (int i = 0; i < O; ++i) part[base + o * O + i] = v16[i];   // dW1
+        for (int i = 0; i < O; ++i) part[base + o * O + i] = v16[i] + v16[8 + i];   // dW1 = dz1^T . (obs_hi + obs_lo)
         part[base + H * O + o] = v16[O];                               // db1
         umma::ld16(trow + C_W4, v16);
         if (no == 0) {

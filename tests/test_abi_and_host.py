@@ -154,7 +154,10 @@ print("rank", rank, "ok")
 def test_gloo_world2_gradient_allreduce(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER.format(root=ROOT))
-    port = 29000 + os.getpid() % 2000
+    import socket
+    with socket.socket() as sk:      # a free port, so parallel / repeated runs never collide
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(script)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT)
