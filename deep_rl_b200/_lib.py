@@ -64,8 +64,13 @@ SIGNATURES = {
     "drl_permutation": (C.c_int, [u32p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
     "drl_adv_stats": (C.c_int, [C.POINTER(NetT), f32p, u32p, C.c_uint32, C.c_uint32, f32p, C.c_void_p, C.c_size_t,
                                 C.c_void_p]),
+    "drl_adv_stats_perm": (C.c_int, [C.POINTER(NetT), f32p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, f32p,
+                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "drl_ppo_minibatch_grad": (C.c_int, [C.POINTER(NetT), f32p, f32p, u32p, C.c_uint32, C.c_uint32, f32p,
                                          C.POINTER(PpoCoefT), f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
+    "drl_ppo_minibatch_update": (C.c_int, [C.POINTER(NetT), f32p, f32p, u32p, C.c_uint32, C.c_uint32, f32p, C.POINTER(PpoCoefT),
+                                           f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                           C.c_double, f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
     "drl_selftest_umma": (C.c_int, [C.c_int32, C.c_int32, f32p, f32p, f32p, C.c_void_p]),
     "drl_clip_adam": (C.c_int, [C.POINTER(NetT), f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_double, C.c_double, f32p, f32p, C.c_void_p]),

@@ -22,6 +22,8 @@ struct GradArgs {
 int launch_grad_reduce(const GradArgs& g, int grid, int P, float* grad_out, float* loss_terms_out, cudaStream_t st);
 
 // tensor-core implementation (update_tc.cu)
-int launch_grad_tc(const drl_net_t* net, const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st);
+// grid_out != nullptr: skip the fold of the partials and report the number of partials instead
+int launch_grad_tc(const drl_net_t* net, const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st,
+                   int* grid_out = nullptr);
 
 }  // namespace drl

@@ -161,6 +161,86 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict_
     }
 }
 
+// Same statistics without the gather: walk the samples in NATURAL order (coalesced 4-byte reads of the advantage
+// plane), invert the keyed Feistel permutation to find each sample's position and hence its minibatch.
+// HBM traffic 4 B/sample instead of a 32-byte sector per gathered sample.
+constexpr int STATS_MAX_MB = 8;
+
+__device__ __forceinline__ uint32_t perm_position(uint32_t s, uint32_t B, uint32_t a, uint32_t b, const uint32_t (&keys)[8]) {
+    uint32_t x = s;
+    do {
+        uint32_t lb = a, rb = b;
+        uint32_t L = x >> rb, R = x & ((1u << rb) - 1u);
+#pragma unroll
+        for (int r = PERM_ROUNDS - 1; r >= 0; --r) {
+            const uint32_t t = lb; lb = rb; rb = t;
+            const uint32_t R0 = L;
+            const uint32_t L0 = R ^ (fmix32(R0 ^ keys[r]) & ((1u << lb) - 1u));
+            L = L0; R = R0;
+        }
+        x = (L << rb) | R;
+    } while (x >= B);
+    return x;
+}
+
+__global__ void __launch_bounds__(256) adv_stats_perm_kernel(const float* __restrict__ adv, uint32_t B, uint32_t mb_size, uint32_t nmb,
+                                                              uint32_t a, uint32_t b, uint64_t seed, uint32_t epoch_ctr, uint32_t rank,
+                                                              float* __restrict__ stats_out, double* __restrict__ partials,
+                                                              uint32_t* __restrict__ counter) {
+    const uint4 k0 = philox_seeded(seed, epoch_ctr, rank, 0u, TAG_PERM);
+    const uint4 k1 = philox_seeded(seed, epoch_ctr, rank, 1u, TAG_PERM);
+    const uint32_t keys[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    double sm_[STATS_MAX_MB], ss_[STATS_MAX_MB];
+#pragma unroll
+    for (int m = 0; m < STATS_MAX_MB; ++m) { sm_[m] = 0.0; ss_[m] = 0.0; }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < B; s += stride) {
+        const double v = (double)__ldg(adv + s);
+        const uint32_t mb = perm_position(s, B, a, b, keys) / mb_size;
+#pragma unroll
+        for (int m = 0; m < STATS_MAX_MB; ++m)
+            if (mb == (uint32_t)m) { sm_[m] += v; ss_[m] = fma(v, v, ss_[m]); }
+    }
+    __shared__ double sh[2][STATS_MAX_MB][8];
+    __shared__ bool is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int m = 0; m < STATS_MAX_MB; ++m) {
+        const double t0 = warp_sum(sm_[m]), t1 = warp_sum(ss_[m]);
+        if (lane == 0) { sh[0][m][warp] = t0; sh[1][m][warp] = t1; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * STATS_MAX_MB) {
+        const int which = threadIdx.x / STATS_MAX_MB, m = threadIdx.x % STATS_MAX_MB;
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[which][m][w];
+        partials[((size_t)m * STAT_PARTS + blockIdx.x) * 2 + which] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < nmb) {
+        __threadfence();
+        const uint32_t k = threadIdx.x;
+        double ts = 0.0, tss = 0.0;
+        for (uint32_t p = 0; p < gridDim.x; ++p) {
+            ts += __ldcg(&partials[((size_t)k * STAT_PARTS + p) * 2 + 0]);
+            tss += __ldcg(&partials[((size_t)k * STAT_PARTS + p) * 2 + 1]);
+        }
+        const uint32_t klo = k * mb_size, khi = min(B, klo + mb_size);
+        const double cnt = (double)(khi - klo);
+        const double mean = ts / cnt;
+        const double var = (tss - ts * mean) / (cnt - 1.0);
+        stats_out[2 * k + 0] = (float)mean;
+        stats_out[2 * k + 1] = (float)sqrt(var > 0.0 ? var : 0.0);
+        if (k == 0) *counter = 0;
+    }
+}
+
 }  // namespace drl
 
 using namespace drl;
@@ -220,6 +300,28 @@ int drl_adv_stats(const drl_net_t* net, const float* rec, const uint32_t* idx, u
     if (net->obs_dim <= 4) adv_stats_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(rec, idx, B, mb_size, stats_out, partials, counter);
     else adv_stats_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(rec, idx, B, mb_size, stats_out, partials, counter);
     DRL_LAUNCH_CHECK("adv_stats_kernel");
+    return DRL_OK;
+}
+
+int drl_adv_stats_perm(const drl_net_t* net, const float* adv, uint32_t B, uint32_t mb_size, uint64_t seed, uint32_t epoch_ctr,
+                       uint32_t rank, float* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_net(net);
+    if (rc != DRL_OK) return rc;
+    DRL_REQUIRE(adv && stats_out && workspace, "drl_adv_stats_perm: NULL pointer");
+    DRL_REQUIRE(B > 0 && mb_size > 0 && B <= 0x80000000u, "drl_adv_stats_perm: B=%u mb_size=%u", B, mb_size);
+    const uint32_t nmb = (B + mb_size - 1) / mb_size;
+    if (nmb > (uint32_t)STATS_MAX_MB) { set_error("drl_adv_stats_perm: %u minibatches > %d (use drl_adv_stats)", nmb, STATS_MAX_MB); return DRL_ERR_UNSUPPORTED; }
+    const WorkspaceLayout w = workspace_layout(drl_param_count(net));
+    DRL_REQUIRE(workspace_bytes >= w.total, "drl_adv_stats_perm: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    uint32_t* counter = reinterpret_cast<uint32_t*>((char*)workspace + w.counters);
+    double* partials = reinterpret_cast<double*>((char*)workspace + w.stat_partials);
+    uint32_t k = 2;
+    while (k < 32 && (1ull << k) < (unsigned long long)B) ++k;
+    uint32_t blocks = (B + 2047u) / 2048u;
+    if (blocks > (uint32_t)STAT_PARTS) blocks = STAT_PARTS;
+    adv_stats_perm_kernel<<<blocks, 256, 0, as_stream(stream)>>>(adv, B, mb_size, nmb, k / 2, k - k / 2, seed, epoch_ctr, rank,
+                                                                 stats_out, partials, counter);
+    DRL_LAUNCH_CHECK("adv_stats_perm_kernel");
     return DRL_OK;
 }
 

@@ -455,8 +455,104 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(AdamArgs a) {
     if (a.packed != nullptr) packed_store<O, A>(a.packed, i, p);
 }
 
+// Single-GPU tail of a minibatch step in ONE cooperative launch: fixed-order fold of the per-CTA partial gradients,
+// global-norm clip and Adam (+ packed-layout refresh).  blockDim = (32, 8): a CTA owns 32 parameters, thread (x, y)
+// folds partials y, y+8, ...; after a grid-wide barrier (all CTAs are co-resident: cooperative launch) every CTA
+// sums the per-CTA squared norms in the same order and applies Adam to its 32 parameters.
+struct FusedArgs {
+    AdamArgs a;
+    const float* grad_part; const float* loss_part; float* grad_out; float* loss_terms_out;
+    double* cta_sumsq; uint32_t* arrive; uint32_t* depart;
+    int nparts, ppad;
+    uint32_t mb_count;
+    float ent_coef, vf_coef;
+};
+
+template <int O, int A>
+__global__ void __launch_bounds__(256) reduce_clip_adam_kernel(FusedArgs f) {
+    __shared__ float sh[8][33];
+    __shared__ double shd[32];
+    __shared__ float s_coef;
+    const int P = f.a.P;
+    const int p = blockIdx.x * 32 + threadIdx.x;
+    float sacc = 0.0f;
+    if (p < P) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int c = threadIdx.y;
+        for (; c + 24 < f.nparts; c += 32) {
+            const float v0 = __ldcg(f.grad_part + (size_t)c * f.ppad + p);
+            const float v1 = __ldcg(f.grad_part + (size_t)(c + 8) * f.ppad + p);
+            const float v2 = __ldcg(f.grad_part + (size_t)(c + 16) * f.ppad + p);
+            const float v3 = __ldcg(f.grad_part + (size_t)(c + 24) * f.ppad + p);
+            a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+        }
+        for (; c < f.nparts; c += 8) a0 += __ldcg(f.grad_part + (size_t)c * f.ppad + p);
+        sacc = (a0 + a1) + (a2 + a3);
+    }
+    sh[threadIdx.y][threadIdx.x] = sacc;
+    __syncthreads();
+    float gval = 0.0f;
+    if (threadIdx.y == 0) {
+        float t = sh[0][threadIdx.x];
+#pragma unroll
+        for (int y = 1; y < 8; ++y) t += sh[y][threadIdx.x];
+        gval = p < P ? t : 0.0f;
+        if (p < P) f.grad_out[p] = gval;
+        const double gs = (double)(gval * f.a.grad_scale);
+        shd[threadIdx.x] = gs * gs;
+    }
+    if (blockIdx.x == 0 && threadIdx.y == 1 && threadIdx.x < 5 && f.loss_terms_out != nullptr) {
+        float t = 0.f;
+        for (int c = 0; c < f.nparts; ++c) t += __ldcg(f.loss_part + c * LOSS_TERMS + threadIdx.x);
+        const float inv = 1.0f / (float)f.mb_count;
+        const float t0 = __shfl_sync(0x1fu, t, 0), t1 = __shfl_sync(0x1fu, t, 1), t2 = __shfl_sync(0x1fu, t, 2);
+        const float t3 = __shfl_sync(0x1fu, t, 3), t4 = __shfl_sync(0x1fu, t, 4);
+        if (threadIdx.x == 0) {
+            const float pg = t0 * inv, vl = 0.5f * t1 * inv, en = t2 * inv;
+            f.loss_terms_out[0] = pg - f.ent_coef * en + vl * f.vf_coef;
+            f.loss_terms_out[1] = pg; f.loss_terms_out[2] = vl; f.loss_terms_out[3] = en;
+            f.loss_terms_out[4] = t3 * inv; f.loss_terms_out[5] = t4 * inv;
+            f.loss_terms_out[6] = 0.0f; f.loss_terms_out[7] = 0.0f;
+        }
+    }
+    __syncthreads();
+    // ---- grid-wide barrier ----
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 32; ++i) t += shd[i];
+        f.cta_sumsq[blockIdx.x] = t;
+        __threadfence();
+        atomicAdd(f.arrive, 1u);
+        while (*reinterpret_cast<volatile uint32_t*>(f.arrive) < gridDim.x) { }
+        __threadfence();
+        double tot = 0.0;
+        for (unsigned i = 0; i < gridDim.x; ++i) tot += __ldcg(f.cta_sumsq + i);
+        const float norm = (float)sqrt(tot);
+        const float cf = f.a.max_norm / (norm + 1e-6f);
+        s_coef = cf < 1.0f ? cf : 1.0f;
+        if (blockIdx.x == 0 && f.a.norm_out) *f.a.norm_out = norm;
+    }
+    __syncthreads();
+    if (threadIdx.y == 0 && p < P) {
+        const AdamArgs& a = f.a;
+        const float gsc = (gval * a.grad_scale) * s_coef;
+        float m = a.m[p], v = a.v[p], w = a.params[p];
+        m = m + a.om_beta1 * (gsc - m);
+        v = v * a.beta2 + (a.om_beta2 * gsc) * gsc;
+        const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+        w = w + (a.neg_step_size * m) / denom;
+        a.m[p] = m; a.v[p] = v; a.params[p] = w;
+        if (a.packed != nullptr) packed_store<O, A>(a.packed, p, w);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();
+        if (atomicAdd(f.depart, 1u) == gridDim.x - 1) { *f.arrive = 0u; *f.depart = 0u; }   // re-arm (stream-ordered)
+    }
+}
+
 template <int O, int A, int OP, int RW>
-int launch_grad(const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st) {
+int launch_grad(const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st, int* grid_out) {
     const size_t smem = sizeof(float) * (Packed<O, A>::ALL + 4 + GW * WS_G);
     DRL_CUDA(cudaFuncSetAttribute(ppo_grad_kernel<O, A, OP, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t ntiles = (g.mb_count + CTA_TILE - 1) / CTA_TILE;
@@ -465,6 +561,7 @@ int launch_grad(const GradArgs& g, int P, float* grad_out, float* loss_terms_out
     if ((uint32_t)grid > ntiles) grid = (int)ntiles;
     ppo_grad_kernel<O, A, OP, RW><<<grid, GT, smem, st>>>(g);
     DRL_LAUNCH_CHECK("ppo_grad_kernel");
+    if (grid_out != nullptr) { *grid_out = grid; return DRL_OK; }   // caller folds the partials itself
     return launch_grad_reduce(g, grid, P, grad_out, loss_terms_out, st);
 }
 
@@ -481,16 +578,14 @@ using namespace drl;
 
 extern "C" {
 
-int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const float* rec, const uint32_t* idx,
-                           uint32_t mb_start, uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef,
-                           float* grad_out, float* loss_terms_out, void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
-    int rc = check_net(net);
-    if (rc != DRL_OK) return rc;
-    DRL_REQUIRE(packed && rec && adv_stats && coef && grad_out && workspace, "drl_ppo_minibatch_grad: NULL pointer");
-    DRL_REQUIRE(mb_count > 0, "drl_ppo_minibatch_grad: empty minibatch");
+static int run_grad(const drl_net_t* net, const float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
+                    uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* grad_out, float* loss_terms_out,
+                    void* workspace, size_t workspace_bytes, uint32_t flags, cudaStream_t st, GradArgs* g_out, int* grid_out) {
+    DRL_REQUIRE(packed && rec && adv_stats && coef && grad_out && workspace, "minibatch gradient: NULL pointer");
+    DRL_REQUIRE(mb_count > 0, "minibatch gradient: empty minibatch");
     const int P = (int)drl_param_count(net);
     const WorkspaceLayout w = workspace_layout(P);
-    DRL_REQUIRE(workspace_bytes >= w.total, "drl_ppo_minibatch_grad: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    DRL_REQUIRE(workspace_bytes >= w.total, "minibatch gradient: workspace %zu < %zu bytes", workspace_bytes, w.total);
     GradArgs g;
     g.packed = packed; g.rec = rec; g.idx = idx; g.mb_start = mb_start; g.mb_count = mb_count; g.adv_stats = adv_stats;
     g.clip_coef = coef->clip_coef; g.ent_coef = coef->ent_coef; g.vf_coef = coef->vf_coef;
@@ -498,9 +593,63 @@ int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const floa
     g.loss_part = reinterpret_cast<float*>((char*)workspace + w.loss_partials);
     g.ppad = w.ppad;
     g.dbg = getenv("DRL_TC_DEBUG") ? reinterpret_cast<long long*>((char*)workspace + w.debug) : nullptr;
-    if (flags & DRL_GRAD_TENSOR_CORES) return launch_grad_tc(net, g, P, grad_out, loss_terms_out, as_stream(stream));
-    if (net->obs_dim == 4) return launch_grad<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, as_stream(stream));
-    return launch_grad<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, as_stream(stream));
+    if (g_out) *g_out = g;
+    if (flags & DRL_GRAD_TENSOR_CORES) return launch_grad_tc(net, g, P, grad_out, loss_terms_out, st, grid_out);
+    if (net->obs_dim == 4) return launch_grad<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, st, grid_out);
+    return launch_grad<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, st, grid_out);
+}
+
+static void fill_adam(AdamArgs& a, const drl_net_t* net, float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
+                      int64_t step, double lr, double beta1, double beta2, double eps, double max_grad_norm, double grad_scale,
+                      float* packed_out, float* norm_out) {
+    a.params = params; a.grad = grad; a.m = exp_avg; a.v = exp_avg_sq; a.packed = packed_out; a.norm_out = norm_out;
+    a.P = (int)drl_param_count(net);
+    a.grad_scale = (float)grad_scale; a.max_norm = (float)max_grad_norm;
+    a.beta2 = (float)beta2; a.om_beta1 = (float)(1.0 - beta1); a.om_beta2 = (float)(1.0 - beta2); a.eps = (float)eps;
+    // scalars exactly as torch.optim.adam._single_tensor_adam computes them (Python floats, fp64)
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    a.neg_step_size = (float)(-(lr / bc1));
+    a.bc2_sqrt = (float)sqrt(bc2);
+}
+
+int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const float* rec, const uint32_t* idx,
+                           uint32_t mb_start, uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef,
+                           float* grad_out, float* loss_terms_out, void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+    int rc = check_net(net);
+    if (rc != DRL_OK) return rc;
+    return run_grad(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, grad_out, loss_terms_out, workspace, workspace_bytes,
+                    flags, as_stream(stream), nullptr, nullptr);
+}
+
+int drl_ppo_minibatch_update(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
+                             uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params, float* grad_out,
+                             float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
+                             double max_grad_norm, float* loss_terms_out, float* norm_out, void* workspace, size_t workspace_bytes,
+                             uint32_t flags, void* stream) {
+    int rc = check_net(net);
+    if (rc != DRL_OK) return rc;
+    DRL_REQUIRE(params && exp_avg && exp_avg_sq, "drl_ppo_minibatch_update: NULL pointer");
+    DRL_REQUIRE(step >= 1, "drl_ppo_minibatch_update: step=%lld must be >= 1", (long long)step);
+    cudaStream_t st = as_stream(stream);
+    GradArgs g;
+    int grid = 0;
+    rc = run_grad(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, grad_out, loss_terms_out, workspace, workspace_bytes,
+                  flags, st, &g, &grid);
+    if (rc != DRL_OK) return rc;
+    const WorkspaceLayout w = workspace_layout(drl_param_count(net));
+    FusedArgs f;
+    fill_adam(f.a, net, params, grad_out, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_grad_norm, 1.0, packed, norm_out);
+    f.grad_part = g.grad_part; f.loss_part = g.loss_part; f.grad_out = grad_out; f.loss_terms_out = loss_terms_out;
+    f.cta_sumsq = reinterpret_cast<double*>((char*)workspace + w.stat_partials);     // free between statistics launches
+    f.arrive = reinterpret_cast<uint32_t*>((char*)workspace + w.counters) + 4;
+    f.depart = f.arrive + 1;
+    f.nparts = grid; f.ppad = g.ppad; f.mb_count = mb_count; f.ent_coef = coef->ent_coef; f.vf_coef = coef->vf_coef;
+    const int blocks = (f.a.P + 31) / 32;
+    void* args[] = {&f};
+    const void* fn = net->obs_dim == 4 ? (const void*)reduce_clip_adam_kernel<4, 2> : (const void*)reduce_clip_adam_kernel<6, 3>;
+    DRL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(32, 8), args, 0, st));
+    return DRL_OK;
 }
 
 int drl_clip_adam(const drl_net_t* net, float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t step,
@@ -511,15 +660,7 @@ int drl_clip_adam(const drl_net_t* net, float* params, const float* grad, float*
     DRL_REQUIRE(params && grad && exp_avg && exp_avg_sq, "drl_clip_adam: NULL pointer");
     DRL_REQUIRE(step >= 1, "drl_clip_adam: step=%lld must be >= 1", (long long)step);
     AdamArgs a;
-    a.params = params; a.grad = grad; a.m = exp_avg; a.v = exp_avg_sq; a.packed = packed_out; a.norm_out = norm_out;
-    a.P = (int)drl_param_count(net);
-    a.grad_scale = (float)grad_scale; a.max_norm = (float)max_grad_norm;
-    a.beta2 = (float)beta2; a.om_beta1 = (float)(1.0 - beta1); a.om_beta2 = (float)(1.0 - beta2); a.eps = (float)eps;
-    // scalars exactly as torch.optim.adam._single_tensor_adam computes them (Python floats, fp64)
-    const double bc1 = 1.0 - pow(beta1, (double)step);
-    const double bc2 = 1.0 - pow(beta2, (double)step);
-    a.neg_step_size = (float)(-(lr / bc1));
-    a.bc2_sqrt = (float)sqrt(bc2);
+    fill_adam(a, net, params, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_grad_norm, grad_scale, packed_out, norm_out);
     const int blocks = (a.P + 255) / 256;
     if (net->obs_dim == 4) clip_adam_kernel<4, 2><<<blocks, 256, 0, as_stream(stream)>>>(a);
     else clip_adam_kernel<6, 3><<<blocks, 256, 0, as_stream(stream)>>>(a);

@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
 }
 
 template <int O, int A, int OP, int RW>
-static int launch_tc(const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st) {
+static int launch_tc(const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st, int* grid_out) {
     const int smem = TcSmem<O, A>::TOTAL;
     DRL_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<O, A, OP, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const uint32_t ntiles = (g.mb_count + TC_TILE - 1) / TC_TILE;
@@ -538,12 +538,14 @@ static int launch_tc(const GradArgs& g, int P, float* grad_out, float* loss_term
     if ((uint32_t)grid > ntiles) grid = (int)ntiles;
     ppo_grad_tc_kernel<O, A, OP, RW><<<grid, TC_THREADS, smem, st>>>(g);
     DRL_LAUNCH_CHECK("ppo_grad_tc_kernel");
+    if (grid_out != nullptr) { *grid_out = grid; return DRL_OK; }
     return launch_grad_reduce(g, grid, P, grad_out, loss_terms_out, st);
 }
 
-int launch_grad_tc(const drl_net_t* net, const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st) {
-    if (net->obs_dim == 4) return launch_tc<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, st);
-    return launch_tc<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, st);
+int launch_grad_tc(const drl_net_t* net, const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st,
+                   int* grid_out) {
+    if (net->obs_dim == 4) return launch_tc<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, st, grid_out);
+    return launch_tc<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, st, grid_out);
 }
 
 }  // namespace drl

@@ -146,6 +146,7 @@ class PPOTrainer:
         self.global_step = 0       # env steps taken on this rank's envs x world (reference counter at N=1)
         self.env.reset()           # ppo.py:101
         self.kernel_launches = 0
+        self.fused_step = True     # single GPU: fold + clip + Adam in one cooperative kernel after the gradient kernel
         self.timing = False        # record CUDA events around each phase (bench.py)
         self.phase_events: Dict[str, list] = {}
 
@@ -194,13 +195,28 @@ class PPOTrainer:
             with _Phase(self, "permutation"):
                 _lib.check(self.L.drl_permutation(self.idx.data_ptr(), B, cfg.seed, epoch_ctr, self.rank, st))
             with _Phase(self, "adv_stats"):
-                _lib.check(self.L.drl_adv_stats(net, self.records.data_ptr(), self.idx.data_ptr(), B, M,
-                                                self.adv_stats.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, st))
+                if self.n_mb <= 8:   # no gather: natural-order pass over the advantage plane + inverse permutation
+                    _lib.check(self.L.drl_adv_stats_perm(net, self.advantages.data_ptr(), B, M, cfg.seed, epoch_ctr, self.rank,
+                                                         self.adv_stats.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, st))
+                else:
+                    _lib.check(self.L.drl_adv_stats(net, self.records.data_ptr(), self.idx.data_ptr(), B, M,
+                                                    self.adv_stats.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, st))
             self.kernel_launches += 2
             for k in range(self.n_mb):
                 start = k * M
                 count = min(M, B - start)
                 row = epoch * self.n_mb + k
+                if self.world == 1 and self.fused_step:
+                    self.adam_step += 1
+                    with _Phase(self, "minibatch_grad"):    # gradient kernel + fused fold/clip/Adam kernel
+                        _lib.check(self.L.drl_ppo_minibatch_update(
+                            net, self.agent.packed.data_ptr(), self.records.data_ptr(), self.idx.data_ptr(), start, count,
+                            self.adv_stats.data_ptr() + 8 * k, C.byref(self.coef), self.agent.flat_params.data_ptr(),
+                            self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.adam_step, lr,
+                            0.9, 0.999, 1e-5, cfg.max_grad_norm, self.loss_terms.data_ptr() + 32 * row,
+                            self.grad_norm.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, self.grad_flags, st))
+                    self.kernel_launches += 2
+                    continue
                 with _Phase(self, "minibatch_grad"):
                     _lib.check(self.L.drl_ppo_minibatch_grad(
                         net, self.agent.packed.data_ptr(), self.records.data_ptr(), self.idx.data_ptr(), start, count,

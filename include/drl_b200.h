@@ -135,11 +135,26 @@ int drl_adv_stats(const drl_net_t* net, const float* rec, const uint32_t* idx, u
 /* ---- loss + backward of one minibatch, ppo.py:159-187 + backward of ppo.py:190 ----
  * grad_out [P] canonical layout, mean over the mb_count samples; loss_terms_out[8] =
  * {loss, pg_loss, v_loss, entropy, approx_kl, clipfrac, 0, 0}. */
+/* Same statistics for the keyed permutation of drl_permutation(seed, epoch_ctr, rank) WITHOUT a gather: adv is the
+ * advantage plane in natural sample order [B]; each sample's minibatch is found by inverting the permutation.
+ * At most 8 minibatches (DRL_ERR_UNSUPPORTED otherwise: use drl_adv_stats). */
+int drl_adv_stats_perm(const drl_net_t* net, const float* adv, uint32_t B, uint32_t mb_size, uint64_t seed, uint32_t epoch_ctr,
+                       uint32_t rank, float* stats_out, void* workspace, size_t workspace_bytes, void* stream);
+
 #define DRL_GRAD_TENSOR_CORES 1u   /* flags: tcgen05 path (bf16 operands, fp32 accumulate) instead of FP32 CUDA cores */
 int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const float* rec, const uint32_t* idx,
                            uint32_t mb_start, uint32_t mb_count, const float* adv_stats /*[2] mean,std*/,
                            const drl_ppo_coef_t* coef, float* grad_out, float* loss_terms_out,
                            void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* ---- single-GPU fusion of the three calls above/below: minibatch gradient, then ONE cooperative kernel that folds
+ * the per-CTA partial gradients, clips by the global norm and applies Adam (ppo.py:159-192 in two launches).
+ * `packed` is read by the gradient kernels and refreshed by the Adam step; grad_out receives the pre-clip gradient. */
+int drl_ppo_minibatch_update(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
+                             uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params, float* grad_out,
+                             float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
+                             double max_grad_norm, float* loss_terms_out, float* norm_out, void* workspace, size_t workspace_bytes,
+                             uint32_t flags, void* stream);
 
 /* ---- clip_grad_norm_ + Adam, ppo.py:191-192 (after the gradient all-reduce) ----
  * grad is multiplied by grad_scale (1/world) first; `step` is the 1-based Adam step of this call.

@@ -45,6 +45,8 @@ def lib() -> C.CDLL:
         L.drl_or_sample.argtypes = [f32p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint64, i32p, f32p]
         L.drl_or_perm_index.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
         L.drl_or_perm_index.restype = C.c_uint32
+        L.drl_or_perm_position.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.drl_or_perm_position.restype = C.c_uint32
         L.drl_or_permutation.argtypes = [u32p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
         L.drl_or_cartpole_step.argtypes = [f64p, C.c_int32]
         L.drl_or_cartpole_step.restype = C.c_int32
