@@ -223,21 +223,28 @@ __global__ void __launch_bounds__(256) adv_stats_perm_kernel(const float* __rest
         is_last = (done == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && threadIdx.x < nmb) {
+    if (is_last) {   // one warp per minibatch folds the partials (lane-strided, then a fixed shuffle tree)
         __threadfence();
-        const uint32_t k = threadIdx.x;
-        double ts = 0.0, tss = 0.0;
-        for (uint32_t p = 0; p < gridDim.x; ++p) {
-            ts += __ldcg(&partials[((size_t)k * STAT_PARTS + p) * 2 + 0]);
-            tss += __ldcg(&partials[((size_t)k * STAT_PARTS + p) * 2 + 1]);
+        const uint32_t k = threadIdx.x >> 5;
+        if (k < nmb) {
+            double ts = 0.0, tss = 0.0;
+            for (uint32_t p = threadIdx.x & 31; p < gridDim.x; p += 32) {
+                ts += __ldcg(&partials[((size_t)k * STAT_PARTS + p) * 2 + 0]);
+                tss += __ldcg(&partials[((size_t)k * STAT_PARTS + p) * 2 + 1]);
+            }
+            ts = warp_sum(ts);
+            tss = warp_sum(tss);
+            if ((threadIdx.x & 31) == 0) {
+                const uint32_t klo = k * mb_size, khi = min(B, klo + mb_size);
+                const double cnt = (double)(khi - klo);
+                const double mean = ts / cnt;
+                const double var = (tss - ts * mean) / (cnt - 1.0);
+                stats_out[2 * k + 0] = (float)mean;
+                stats_out[2 * k + 1] = (float)sqrt(var > 0.0 ? var : 0.0);
+            }
         }
-        const uint32_t klo = k * mb_size, khi = min(B, klo + mb_size);
-        const double cnt = (double)(khi - klo);
-        const double mean = ts / cnt;
-        const double var = (tss - ts * mean) / (cnt - 1.0);
-        stats_out[2 * k + 0] = (float)mean;
-        stats_out[2 * k + 1] = (float)sqrt(var > 0.0 ? var : 0.0);
-        if (k == 0) *counter = 0;
+        __syncthreads();
+        if (threadIdx.x == 0) *counter = 0;
     }
 }
 

@@ -516,21 +516,27 @@ __global__ void __launch_bounds__(256) reduce_clip_adam_kernel(FusedArgs f) {
         }
     }
     __syncthreads();
-    // ---- grid-wide barrier ----
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        double t = 0.0;
-        for (int i = 0; i < 32; ++i) t += shd[i];
-        f.cta_sumsq[blockIdx.x] = t;
-        __threadfence();
-        atomicAdd(f.arrive, 1u);
-        while (*reinterpret_cast<volatile uint32_t*>(f.arrive) < gridDim.x) { }
-        __threadfence();
+    // ---- grid-wide barrier, then every CTA folds the per-CTA squared norms in the same (lane-strided) order ----
+    if (threadIdx.y == 0) {
+        double t = shd[threadIdx.x];
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            f.cta_sumsq[blockIdx.x] = t;
+            __threadfence();
+            atomicAdd(f.arrive, 1u);
+            while (*reinterpret_cast<volatile uint32_t*>(f.arrive) < gridDim.x) { }
+            __threadfence();
+        }
+        __syncwarp();
         double tot = 0.0;
-        for (unsigned i = 0; i < gridDim.x; ++i) tot += __ldcg(f.cta_sumsq + i);
-        const float norm = (float)sqrt(tot);
-        const float cf = f.a.max_norm / (norm + 1e-6f);
-        s_coef = cf < 1.0f ? cf : 1.0f;
-        if (blockIdx.x == 0 && f.a.norm_out) *f.a.norm_out = norm;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) tot += __ldcg(f.cta_sumsq + i);
+        tot = warp_sum(tot);
+        if (threadIdx.x == 0) {
+            const float norm = (float)sqrt(tot);
+            const float cf = f.a.max_norm / (norm + 1e-6f);
+            s_coef = cf < 1.0f ? cf : 1.0f;
+            if (blockIdx.x == 0 && f.a.norm_out) *f.a.norm_out = norm;
+        }
     }
     __syncthreads();
     if (threadIdx.y == 0 && p < P) {
