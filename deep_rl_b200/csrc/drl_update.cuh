@@ -5,6 +5,22 @@
 
 namespace drl {
 
+struct AdamArgs {
+    float* params; const float* grad; float* m; float* v; float* packed; float* norm_out;
+    int P;
+    float grad_scale, max_norm, beta2, om_beta1, om_beta2, eps, neg_step_size, bc2_sqrt;
+};
+
+// Optional in-kernel tail of the tensor-core gradient kernel (single GPU): after a grid-wide barrier the CTAs fold
+// the partial gradients slice-wise, clip by the global norm and apply Adam -- the whole minibatch step is one launch.
+struct TailArgs {
+    int enabled;
+    AdamArgs a;
+    float* grad_out; float* loss_terms_out;
+    double* cta_sumsq;        // [gridDim.x]
+    uint32_t* ctr;            // [3] arrive-1, arrive-2, depart (zero between launches)
+};
+
 struct GradArgs {
     const float* packed;
     const float* rec;
@@ -16,6 +32,7 @@ struct GradArgs {
     float* loss_part;         // [gridDim.x][LOSS_TERMS]
     int ppad;
     long long* dbg;           // optional cycle stamps (diagnostics), else nullptr
+    TailArgs tail;
 };
 
 // fixed-order fold of `grid` per-CTA partial gradients / loss sums (update_ops.cu)
@@ -25,5 +42,7 @@ int launch_grad_reduce(const GradArgs& g, int grid, int P, float* grad_out, floa
 // grid_out != nullptr: skip the fold of the partials and report the number of partials instead
 int launch_grad_tc(const drl_net_t* net, const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st,
                    int* grid_out = nullptr);
+// tensor-core gradient + in-kernel fold / clip / Adam tail (g.tail filled by the caller), one cooperative launch
+int launch_grad_tc_fused(const drl_net_t* net, GradArgs& g, cudaStream_t st);
 
 }  // namespace drl

@@ -402,12 +402,6 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const float* __restric
 
 // clip_grad_norm_ + Adam.  Every CTA recomputes the global norm from the (L2-resident) gradient in
 // the same order, so no grid-wide synchronisation is needed and all CTAs agree bit-for-bit.
-struct AdamArgs {
-    float* params; const float* grad; float* m; float* v; float* packed; float* norm_out;
-    int P;
-    float grad_scale, max_norm, beta2, om_beta1, om_beta2, eps, neg_step_size, bc2_sqrt;
-};
-
 template <int O, int A>
 __global__ void __launch_bounds__(256) clip_adam_kernel(AdamArgs a) {
     __shared__ double sh[8];
@@ -599,7 +593,8 @@ static int run_grad(const drl_net_t* net, const float* packed, const float* rec,
     g.loss_part = reinterpret_cast<float*>((char*)workspace + w.loss_partials);
     g.ppad = w.ppad;
     g.dbg = getenv("DRL_TC_DEBUG") ? reinterpret_cast<long long*>((char*)workspace + w.debug) : nullptr;
-    if (g_out) *g_out = g;
+    g.tail.enabled = 0;
+    if (g_out) { *g_out = g; if (grid_out == nullptr) return DRL_OK; }   // arguments only
     if (flags & DRL_GRAD_TENSOR_CORES) return launch_grad_tc(net, g, P, grad_out, loss_terms_out, st, grid_out);
     if (net->obs_dim == 4) return launch_grad<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, st, grid_out);
     return launch_grad<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, st, grid_out);
@@ -640,10 +635,21 @@ int drl_ppo_minibatch_update(const drl_net_t* net, float* packed, const float* r
     cudaStream_t st = as_stream(stream);
     GradArgs g;
     int grid = 0;
+    const WorkspaceLayout w = workspace_layout(drl_param_count(net));
+    if (flags & DRL_GRAD_TENSOR_CORES) {   // one cooperative launch: gradient + fold + clip + Adam
+        rc = run_grad(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, grad_out, loss_terms_out, workspace, workspace_bytes,
+                      flags, st, &g, nullptr);
+        if (rc != DRL_OK) return rc;
+        g.tail.enabled = 1;
+        fill_adam(g.tail.a, net, params, grad_out, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_grad_norm, 1.0, packed, norm_out);
+        g.tail.grad_out = grad_out; g.tail.loss_terms_out = loss_terms_out;
+        g.tail.cta_sumsq = reinterpret_cast<double*>((char*)workspace + w.stat_partials);
+        g.tail.ctr = reinterpret_cast<uint32_t*>((char*)workspace + w.counters) + 8;
+        return launch_grad_tc_fused(net, g, st);
+    }
     rc = run_grad(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, grad_out, loss_terms_out, workspace, workspace_bytes,
                   flags, st, &g, &grid);
     if (rc != DRL_OK) return rc;
-    const WorkspaceLayout w = workspace_layout(drl_param_count(net));
     FusedArgs f;
     fill_adam(f.a, net, params, grad_out, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_grad_norm, 1.0, packed, norm_out);
     f.grad_part = g.grad_part; f.loss_part = g.loss_part; f.grad_out = grad_out; f.loss_terms_out = loss_terms_out;

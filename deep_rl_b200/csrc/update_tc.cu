@@ -526,6 +526,127 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         else if (tid == 8) part[P::C_ACTOR + P::C_NET + H] = sv;                    // critic head bias
     }
     if (warp == 1) umma::tmem_dealloc(tmem, TC_COLS);
+    if (!g.tail.enabled) return;
+
+    // ================= in-kernel tail (single GPU): fold partials, clip, Adam =================
+    // Only the 512 compute threads are left (the issuer warp has returned): named barrier 13, count 512.
+    constexpr uint32_t BAR_TAIL = 13;
+    const TailArgs& tl = g.tail;
+    const AdamArgs& ad = tl.a;
+    const int PP = ad.P;
+    const int nparts = gridDim.x;
+    float* tred = reinterpret_cast<float*>(sm + S::OFF_H1);              // [8][64] fold scratch (tiles are dead now)
+    double* dred = reinterpret_cast<double*>(sm + S::OFF_H1 + 4096);     // [16] warp partials of the squared norm
+    float* sbc = reinterpret_cast<float*>(sm + S::OFF_H1 + 8192);        // broadcast slot
+    __threadfence();
+    named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    if (tid == 0) {
+        atomicAdd(tl.ctr + 0, 1u);
+        while (*reinterpret_cast<volatile uint32_t*>(tl.ctr + 0) < gridDim.x) { }
+        __threadfence();
+    }
+    named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    const int chunk = (PP + nparts - 1) / nparts;
+    const int p_lo = blockIdx.x * chunk, p_hi = min(PP, p_lo + chunk);
+    const int pl = tid & 63, sl = tid >> 6;        // parameter within a group of 64, slice of the partials (8 slices)
+    double sq = 0.0;
+    for (int p0 = p_lo; p0 < p_hi; p0 += 64) {
+        const int p = p0 + pl;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (p < p_hi) {
+            int c = sl;
+            for (; c + 24 < nparts; c += 32) {
+                const float v0 = __ldcg(g.grad_part + (size_t)c * g.ppad + p);
+                const float v1 = __ldcg(g.grad_part + (size_t)(c + 8) * g.ppad + p);
+                const float v2 = __ldcg(g.grad_part + (size_t)(c + 16) * g.ppad + p);
+                const float v3 = __ldcg(g.grad_part + (size_t)(c + 24) * g.ppad + p);
+                a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+            }
+            for (; c < nparts; c += 8) a0 += __ldcg(g.grad_part + (size_t)c * g.ppad + p);
+        }
+        tred[sl * 64 + pl] = (a0 + a1) + (a2 + a3);
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+        if (sl == 0 && p < p_hi) {
+            float t = tred[pl];
+#pragma unroll
+            for (int y = 1; y < 8; ++y) t += tred[y * 64 + pl];
+            tl.grad_out[p] = t;
+            const double gs = (double)(t * ad.grad_scale);
+            sq = fma(gs, gs, sq);
+        }
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) dred[warp] = sq;
+    named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    if (tid == 0) {
+        double t = 0.0;
+        for (int wv = 0; wv < TC_COMPUTE / 32; ++wv) t += dred[wv];
+        tl.cta_sumsq[blockIdx.x] = t;
+        __threadfence();
+        atomicAdd(tl.ctr + 1, 1u);
+        while (*reinterpret_cast<volatile uint32_t*>(tl.ctr + 1) < gridDim.x) { }
+        __threadfence();
+    }
+    named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    if (warp == 0) {
+        double tot = 0.0;
+        for (int i = lane; i < nparts; i += 32) tot += __ldcg(tl.cta_sumsq + i);
+        tot = warp_sum(tot);
+        if (lane == 0) {
+            const float norm = (float)sqrt(tot);
+            const float cf = ad.max_norm / (norm + 1e-6f);
+            sbc[0] = cf < 1.0f ? cf : 1.0f;
+            if (blockIdx.x == 0 && ad.norm_out) *ad.norm_out = norm;
+        }
+    } else if (blockIdx.x == 0 && warp >= 1 && warp <= 5 && tl.loss_terms_out != nullptr) {
+        float t = 0.f;                                    // warp w folds loss term w-1 over the CTAs
+        for (int c = lane; c < nparts; c += 32) t += __ldcg(g.loss_part + c * LOSS_TERMS + (warp - 1));
+        t = warp_sum(t);
+        if (lane == 0) sbc[4 + warp - 1] = t;
+    }
+    named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    const float coef = sbc[0];
+    for (int p = p_lo + tid; p < p_hi; p += TC_COMPUTE) {
+        const float gsc = (__ldcg(tl.grad_out + p) * ad.grad_scale) * coef;
+        float m = ad.m[p], v = ad.v[p], wgt = ad.params[p];
+        m = m + ad.om_beta1 * (gsc - m);
+        v = v * ad.beta2 + (ad.om_beta2 * gsc) * gsc;
+        const float denom = sqrtf(v) / ad.bc2_sqrt + ad.eps;
+        wgt = wgt + (ad.neg_step_size * m) / denom;
+        ad.m[p] = m; ad.v[p] = v; ad.params[p] = wgt;
+        if (ad.packed != nullptr) packed_store<O, A>(ad.packed, p, wgt);
+    }
+    if (blockIdx.x == 0 && tid == 0 && tl.loss_terms_out != nullptr) {
+        const float inv = 1.0f / (float)g.mb_count;
+        const float pg = sbc[4] * inv, vl = 0.5f * sbc[5] * inv, en = sbc[6] * inv;
+        tl.loss_terms_out[0] = pg - g.ent_coef * en + vl * g.vf_coef;
+        tl.loss_terms_out[1] = pg; tl.loss_terms_out[2] = vl; tl.loss_terms_out[3] = en;
+        tl.loss_terms_out[4] = sbc[7] * inv; tl.loss_terms_out[5] = sbc[8] * inv;
+        tl.loss_terms_out[6] = 0.0f; tl.loss_terms_out[7] = 0.0f;
+    }
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(tl.ctr + 2, 1u) == gridDim.x - 1) { tl.ctr[0] = 0u; tl.ctr[1] = 0u; tl.ctr[2] = 0u; }   // re-arm
+    }
+}
+
+template <int O, int A, int OP, int RW>
+static int launch_tc_fused(GradArgs& g, cudaStream_t st) {
+    const int smem = TcSmem<O, A>::TOTAL;
+    DRL_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<O, A, OP, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const uint32_t ntiles = (g.mb_count + TC_TILE - 1) / TC_TILE;
+    int grid = sm_count();
+    if (grid > MAX_GRAD_CTAS) grid = MAX_GRAD_CTAS;
+    if ((uint32_t)grid > ntiles) grid = (int)ntiles;
+    void* args[] = {&g};
+    DRL_CUDA(cudaLaunchCooperativeKernel((const void*)ppo_grad_tc_kernel<O, A, OP, RW>, dim3(grid), dim3(TC_THREADS), args, (size_t)smem, st));
+    return DRL_OK;
+}
+
+int launch_grad_tc_fused(const drl_net_t* net, GradArgs& g, cudaStream_t st) {
+    if (net->obs_dim == 4) return launch_tc_fused<4, 2, 4, 8>(g, st);
+    return launch_tc_fused<6, 3, 8, 16>(g, st);
 }
 
 template <int O, int A, int OP, int RW>
