@@ -160,6 +160,7 @@ def run_b200(args):
                     update_precision=args.precision)
     tr = PPOTrainer(cfg, rank=rank, world=world, device=dev)
     nu = cfg.num_updates(world)
+    n_mb = tr.n_mb
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     for _ in range(max(3, args.warmup)):
@@ -229,12 +230,36 @@ def run_b200(args):
                 "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "flops_per_launch": flops_per_launch, "launch_ms": g["mean_ms"],
                 "note": ("tcgen05 path: the three HxH GEMMs and all weight-gradient reductions run on the tensor pipe (bf16 operands, "
-                         "fp32 TMEM accumulators); FLOPs counted are the algorithmic 3F per sample" if tc else
+                         "fp32 TMEM accumulators); FLOPs counted are the algorithmic 3F per sample; launch_ms is the whole minibatch-step "
+                         "call (on one GPU the gradient kernel carries the fold + clip + Adam tail)" if tc else
                          "FP32 CUDA-core (FFMA) path; the tensor-pipe peak is the roof the tcgen05 path is held to"),
                 "hbm": {"achieved_gbs": GRAD_BYTES_PER_SAMPLE[args.env_id] * M / (g["mean_ms"] * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"]},
                 "end_to_end": {"hbm_frac": value * BYTES_PER_ENV_STEP[args.env_id] / world / 1e9 / peaks["hbm_gbs"],
                                "tensor_frac": value * 13 * F / world / 1e12 / peaks["bf16_tflops_sustained"]},
                 "share_of_step": g["total_ms"] / max(1e-9, sum(a.elapsed_time(b) for a, b in evs))}
+
+    # ---- N = 1 only: the multi-GPU workload (C3) on this one GPU, so that scaling can be read off like-for-like ----
+    scaling_ref = None
+    if world == 1 and envs == 4096 and args.env_id == "CartPole-v1" and not args.no_scaling_reference:
+        del tr
+        torch.cuda.empty_cache()
+        cfg3 = PPOConfig(env_id=args.env_id, num_envs=65_536, num_steps=T, total_timesteps=65_536 * T * 64, seed=1,
+                         update_precision=args.precision)
+        tr3 = PPOTrainer(cfg3, rank=0, world=1, device=dev)
+        for _ in range(3):
+            tr3.update(64)
+        torch.cuda.synchronize()
+        ev3 = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); tr3.update(64); e1.record()
+            ev3.append((e0, e1))
+        torch.cuda.synchronize()
+        ms3 = sum(a.elapsed_time(b) for a, b in ev3) / 5
+        scaling_ref = {"workload": "C3 (65,536 envs x 128 steps) on this one GPU: the per-GPU work of the N>1 runs",
+                       "value": 65_536 * T / (ms3 * 1e-3), "unit": "env-steps/s", "ms_per_step": ms3, "steps": 5}
+        del tr3
 
     if rank != 0:
         dist.shutdown()
@@ -255,7 +280,7 @@ def run_b200(args):
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tc else "f32", "data": "synthetic",
         "config": {"workload": workload, "precision": ("update GEMMs bf16 x bf16 -> fp32 on tcgen05; rollout, env, GAE, loss, Adam fp32/fp64" if tc else "fp32"), "env_id": args.env_id, "envs_per_gpu": envs, "num_steps": T, "hidden": 64,
-                   "minibatch_size": M, "update_epochs": cfg.update_epochs, "optimizer_steps_per_update": cfg.update_epochs * tr.n_mb,
+                   "minibatch_size": M, "update_epochs": cfg.update_epochs, "optimizer_steps_per_update": cfg.update_epochs * n_mb,
                    "parallelism": f"env-sharded x{world}", "l2": "flushed between updates (256 MiB memset outside the timed events); "
                    "every update regenerates its own rollout data"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / args.steps,
@@ -264,6 +289,7 @@ def run_b200(args):
                         "only per-update host inputs are kernel arguments (no tensor H2D)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "phases_ms_per_update": {k: v["total_ms"] / args.steps for k, v in phases.items()},
+        "scaling_reference": scaling_ref,
     }
     print(json.dumps(line), flush=True)
     dist.shutdown()
@@ -280,6 +306,7 @@ def main():
     ap.add_argument("--env-id", default="CartPole-v1")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scaling-reference", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="update GEMMs: bf16 = tcgen05 tensor cores (bf16 operands, fp32 accumulate), fp32 = CUDA cores")
     args = ap.parse_args()
