@@ -36,6 +36,11 @@ class RolloutBufT(C.Structure):
                 ("rew", C.c_void_p), ("done", C.c_void_p)]
 
 
+class CommT(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("peer", C.c_void_p * 8), ("seq", C.c_uint32),
+                ("error_flag", C.c_void_p)]
+
+
 class PpoCoefT(C.Structure):
     _fields_ = [("clip_coef", C.c_float), ("ent_coef", C.c_float), ("vf_coef", C.c_float)]
 
@@ -71,6 +76,15 @@ SIGNATURES = {
     "drl_ppo_minibatch_update": (C.c_int, [C.POINTER(NetT), f32p, f32p, u32p, C.c_uint32, C.c_uint32, f32p, C.POINTER(PpoCoefT),
                                            f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                            C.c_double, f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
+    "drl_ppo_minibatch_update_dist": (C.c_int, [C.POINTER(NetT), f32p, f32p, u32p, C.c_uint32, C.c_uint32, f32p, C.POINTER(PpoCoefT),
+                                                f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                C.c_double, f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(CommT),
+                                                C.c_void_p]),
+    "drl_comm_bytes": (C.c_size_t, [C.POINTER(NetT)]),
+    "drl_comm_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "drl_comm_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "drl_comm_close": (C.c_int, [C.c_void_p]),
+    "drl_comm_free": (C.c_int, [C.c_void_p]),
     "drl_selftest_umma": (C.c_int, [C.c_int32, C.c_int32, f32p, f32p, f32p, C.c_void_p]),
     "drl_clip_adam": (C.c_int, [C.POINTER(NetT), f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_double, C.c_double, f32p, f32p, C.c_void_p]),

@@ -18,8 +18,26 @@ struct TailArgs {
     AdamArgs a;
     float* grad_out; float* loss_terms_out;
     double* cta_sumsq;        // [gridDim.x]
-    uint32_t* ctr;            // [3] arrive-1, arrive-2, depart (zero between launches)
+    uint32_t* ctr;            // [4] grid barriers 1-3, depart (zero between launches)
+    // multi-GPU (world > 1): symmetric peer buffers, layout = CommLayout
+    int world, rank;
+    unsigned char* peer[DRL_MAX_RANKS];
+    uint32_t seq;
+    int* error_flag;
 };
+
+// symmetric buffer: two generations (seq & 1) of the folded local gradient, then two generations of arrival flags
+struct CommLayout {
+    size_t xgrad[2], flags[2], total;
+};
+__host__ __device__ inline CommLayout comm_layout(int64_t P) {
+    CommLayout c;
+    const size_t g = ((size_t)P * 4 + 255) / 256 * 256;
+    c.xgrad[0] = 0; c.xgrad[1] = g;
+    c.flags[0] = 2 * g; c.flags[1] = 2 * g + 128;
+    c.total = 2 * g + 256;
+    return c;
+}
 
 struct GradArgs {
     const float* packed;

@@ -623,11 +623,11 @@ int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const floa
                     flags, as_stream(stream), nullptr, nullptr);
 }
 
-int drl_ppo_minibatch_update(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
-                             uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params, float* grad_out,
-                             float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
-                             double max_grad_norm, float* loss_terms_out, float* norm_out, void* workspace, size_t workspace_bytes,
-                             uint32_t flags, void* stream) {
+static int minibatch_update_impl(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
+                                 uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params, float* grad_out,
+                                 float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
+                                 double max_grad_norm, float* loss_terms_out, float* norm_out, void* workspace, size_t workspace_bytes,
+                                 uint32_t flags, const drl_comm_t* comm, void* stream) {
     int rc = check_net(net);
     if (rc != DRL_OK) return rc;
     DRL_REQUIRE(params && exp_avg && exp_avg_sq, "drl_ppo_minibatch_update: NULL pointer");
@@ -636,17 +636,24 @@ int drl_ppo_minibatch_update(const drl_net_t* net, float* packed, const float* r
     GradArgs g;
     int grid = 0;
     const WorkspaceLayout w = workspace_layout(drl_param_count(net));
-    if (flags & DRL_GRAD_TENSOR_CORES) {   // one cooperative launch: gradient + fold + clip + Adam
+    if (flags & DRL_GRAD_TENSOR_CORES) {   // one cooperative launch: gradient + fold + [peer all-reduce] + clip + Adam
         rc = run_grad(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, grad_out, loss_terms_out, workspace, workspace_bytes,
                       flags, st, &g, nullptr);
         if (rc != DRL_OK) return rc;
+        const int world = comm ? comm->world : 1;
         g.tail.enabled = 1;
-        fill_adam(g.tail.a, net, params, grad_out, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_grad_norm, 1.0, packed, norm_out);
+        fill_adam(g.tail.a, net, params, grad_out, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_grad_norm, 1.0 / world, packed,
+                  norm_out);
         g.tail.grad_out = grad_out; g.tail.loss_terms_out = loss_terms_out;
         g.tail.cta_sumsq = reinterpret_cast<double*>((char*)workspace + w.stat_partials);
         g.tail.ctr = reinterpret_cast<uint32_t*>((char*)workspace + w.counters) + 8;
+        g.tail.world = world; g.tail.rank = comm ? comm->rank : 0; g.tail.seq = comm ? comm->seq : 0;
+        g.tail.error_flag = comm ? comm->error_flag : nullptr;
+        for (int r = 0; r < DRL_MAX_RANKS; ++r)
+            g.tail.peer[r] = (comm && r < world) ? reinterpret_cast<unsigned char*>(comm->peer[r]) : nullptr;
         return launch_grad_tc_fused(net, g, st);
     }
+    DRL_REQUIRE(comm == nullptr, "drl_ppo_minibatch_update: the fp32 path has no fused multi-GPU form");
     rc = run_grad(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, grad_out, loss_terms_out, workspace, workspace_bytes,
                   flags, st, &g, &grid);
     if (rc != DRL_OK) return rc;
@@ -661,6 +668,64 @@ int drl_ppo_minibatch_update(const drl_net_t* net, float* packed, const float* r
     void* args[] = {&f};
     const void* fn = net->obs_dim == 4 ? (const void*)reduce_clip_adam_kernel<4, 2> : (const void*)reduce_clip_adam_kernel<6, 3>;
     DRL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(32, 8), args, 0, st));
+    return DRL_OK;
+}
+
+int drl_ppo_minibatch_update(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
+                             uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params, float* grad_out,
+                             float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
+                             double max_grad_norm, float* loss_terms_out, float* norm_out, void* workspace, size_t workspace_bytes,
+                             uint32_t flags, void* stream) {
+    return minibatch_update_impl(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, params, grad_out, exp_avg, exp_avg_sq, step,
+                                 lr, beta1, beta2, eps, max_grad_norm, loss_terms_out, norm_out, workspace, workspace_bytes, flags,
+                                 nullptr, stream);
+}
+
+int drl_ppo_minibatch_update_dist(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
+                                  uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params,
+                                  float* grad_out, float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1,
+                                  double beta2, double eps, double max_grad_norm, float* loss_terms_out, float* norm_out,
+                                  void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm, void* stream) {
+    DRL_REQUIRE(comm != nullptr, "drl_ppo_minibatch_update_dist: comm is NULL");
+    DRL_REQUIRE(comm->world >= 1 && comm->world <= DRL_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world,
+                "drl_ppo_minibatch_update_dist: world=%d rank=%d", comm->world, comm->rank);
+    DRL_REQUIRE(flags & DRL_GRAD_TENSOR_CORES, "drl_ppo_minibatch_update_dist: tensor-core path only");
+    for (int r = 0; r < comm->world; ++r) DRL_REQUIRE(comm->peer[r] != nullptr, "drl_ppo_minibatch_update_dist: peer[%d] is NULL", r);
+    return minibatch_update_impl(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, params, grad_out, exp_avg, exp_avg_sq, step,
+                                 lr, beta1, beta2, eps, max_grad_norm, loss_terms_out, norm_out, workspace, workspace_bytes, flags,
+                                 comm, stream);
+}
+
+size_t drl_comm_bytes(const drl_net_t* net) {
+    if (check_net(net) != DRL_OK) return 0;
+    return comm_layout(drl_param_count(net)).total;
+}
+int drl_comm_alloc(size_t bytes, void** dev_ptr_out, void* ipc_handle_out) {
+    DRL_REQUIRE(dev_ptr_out && ipc_handle_out && bytes > 0, "drl_comm_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    void* p = nullptr;
+    DRL_CUDA(cudaMalloc(&p, bytes));
+    DRL_CUDA(cudaMemset(p, 0, bytes));
+    DRL_CUDA(cudaDeviceSynchronize());
+    DRL_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(ipc_handle_out), p));
+    *dev_ptr_out = p;
+    return DRL_OK;
+}
+int drl_comm_open(const void* ipc_handle, void** peer_ptr_out) {
+    DRL_REQUIRE(ipc_handle && peer_ptr_out, "drl_comm_open: NULL pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    DRL_CUDA(cudaIpcOpenMemHandle(peer_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return DRL_OK;
+}
+int drl_comm_close(void* peer_ptr) {
+    DRL_REQUIRE(peer_ptr, "drl_comm_close: NULL pointer");
+    DRL_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return DRL_OK;
+}
+int drl_comm_free(void* dev_ptr) {
+    DRL_REQUIRE(dev_ptr, "drl_comm_free: NULL pointer");
+    DRL_CUDA(cudaFree(dev_ptr));
     return DRL_OK;
 }
 

@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     if (warp == 1) umma::tmem_dealloc(tmem, TC_COLS);
     if (!g.tail.enabled) return;
 
-    // ================= in-kernel tail (single GPU): fold partials, clip, Adam =================
+    // ================= in-kernel tail: fold partials, [all-reduce over NVLink peer memory], clip, Adam =================
     // Only the 512 compute threads are left (the issuer warp has returned): named barrier 13, count 512.
     constexpr uint32_t BAR_TAIL = 13;
     const TailArgs& tl = g.tail;
@@ -538,17 +538,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     float* tred = reinterpret_cast<float*>(sm + S::OFF_H1);              // [8][64] fold scratch (tiles are dead now)
     double* dred = reinterpret_cast<double*>(sm + S::OFF_H1 + 4096);     // [16] warp partials of the squared norm
     float* sbc = reinterpret_cast<float*>(sm + S::OFF_H1 + 8192);        // broadcast slot
-    __threadfence();
-    named_bar_sync(BAR_TAIL, TC_COMPUTE);
-    if (tid == 0) {
-        atomicAdd(tl.ctr + 0, 1u);
-        while (*reinterpret_cast<volatile uint32_t*>(tl.ctr + 0) < gridDim.x) { }
+    auto grid_barrier = [&](uint32_t* ctr) {      // all CTAs are co-resident (cooperative launch)
         __threadfence();
-    }
-    named_bar_sync(BAR_TAIL, TC_COMPUTE);
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+        if (tid == 0) {
+            atomicAdd(ctr, 1u);
+            while (*reinterpret_cast<volatile uint32_t*>(ctr) < gridDim.x) { }
+            __threadfence();
+        }
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    };
+    grid_barrier(tl.ctr + 0);                     // every CTA's partial gradient is in global memory
     const int chunk = (PP + nparts - 1) / nparts;
     const int p_lo = blockIdx.x * chunk, p_hi = min(PP, p_lo + chunk);
     const int pl = tid & 63, sl = tid >> 6;        // parameter within a group of 64, slice of the partials (8 slices)
+    const bool multi = tl.world > 1;
+    const CommLayout cl = comm_layout(PP);
+    const uint32_t gen = tl.seq & 1u;
+    float* xg_local = multi ? reinterpret_cast<float*>(tl.peer[tl.rank] + cl.xgrad[gen]) : nullptr;
     double sq = 0.0;
     for (int p0 = p_lo; p0 < p_hi; p0 += 64) {
         const int p = p0 + pl;
@@ -570,11 +577,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
             float t = tred[pl];
 #pragma unroll
             for (int y = 1; y < 8; ++y) t += tred[y * 64 + pl];
+            if (multi) {
+                xg_local[p] = t;                                  // published to the peers below
+            } else {
+                tl.grad_out[p] = t;
+                const double gs = (double)(t * ad.grad_scale);
+                sq = fma(gs, gs, sq);
+            }
+        }
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    }
+    if (multi) {
+        // ---- one-shot all-reduce over NVLink: publish, signal every peer, wait for every peer, sum in rank order ----
+        __threadfence_system();
+        grid_barrier(tl.ctr + 1);                 // this rank's whole gradient is in its symmetric buffer
+        if (blockIdx.x == 0 && tid < tl.world) {
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(tl.peer[tid] + cl.flags[gen] + 4 * tl.rank) = tl.seq;
+        }
+        if (tid < tl.world) {
+            const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(tl.peer[tl.rank] + cl.flags[gen] + 4 * tid);
+            const long long t0 = clock64();
+            while (*f < tl.seq) {
+                if (clock64() - t0 > 8000000000ll) { if (tl.error_flag) *tl.error_flag = 1; break; }   // ~4 s: a peer is gone
+            }
+            __threadfence_system();
+        }
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+        for (int p = p_lo + tid; p < p_hi; p += TC_COMPUTE) {
+            float t = 0.0f;
+            for (int rk = 0; rk < tl.world; ++rk)
+                t += __ldcg(reinterpret_cast<const float*>(tl.peer[rk] + cl.xgrad[gen]) + p);
             tl.grad_out[p] = t;
             const double gs = (double)(t * ad.grad_scale);
             sq = fma(gs, gs, sq);
         }
-        named_bar_sync(BAR_TAIL, TC_COMPUTE);
     }
     sq = warp_sum(sq);
     if (lane == 0) dred[warp] = sq;
@@ -583,12 +620,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         double t = 0.0;
         for (int wv = 0; wv < TC_COMPUTE / 32; ++wv) t += dred[wv];
         tl.cta_sumsq[blockIdx.x] = t;
-        __threadfence();
-        atomicAdd(tl.ctr + 1, 1u);
-        while (*reinterpret_cast<volatile uint32_t*>(tl.ctr + 1) < gridDim.x) { }
-        __threadfence();
     }
-    named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    grid_barrier(tl.ctr + 2);                     // every CTA's squared-norm share is published
     if (warp == 0) {
         double tot = 0.0;
         for (int i = lane; i < nparts; i += 32) tot += __ldcg(tl.cta_sumsq + i);
@@ -627,7 +660,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     }
     if (tid == 0) {
         __threadfence();
-        if (atomicAdd(tl.ctr + 2, 1u) == gridDim.x - 1) { tl.ctr[0] = 0u; tl.ctr[1] = 0u; tl.ctr[2] = 0u; }   // re-arm
+        if (atomicAdd(tl.ctr + 3, 1u) == gridDim.x - 1) { tl.ctr[0] = 0u; tl.ctr[1] = 0u; tl.ctr[2] = 0u; tl.ctr[3] = 0u; }   // re-arm
     }
 }
 

@@ -66,6 +66,59 @@ def barrier() -> None:
         td.barrier()
 
 
+class PeerComm:
+    """Symmetric peer-memory buffers for the fused multi-GPU minibatch step (drl_comm_t): every rank allocates one
+    IPC-exportable buffer, the handles travel through torch.distributed, and each rank maps all peers' buffers so
+    the gradient kernel can read them over NVLink.  One node only."""
+
+    def __init__(self, net, rank: int, world: int, device):
+        import ctypes as C
+
+        from . import _lib
+        if world > 8:
+            raise ValueError("PeerComm supports up to 8 ranks on one node")
+        self.L = _lib.lib()
+        self.rank, self.world = rank, world
+        nbytes = int(self.L.drl_comm_bytes(C.byref(net)))
+        self.own = C.c_void_p()
+        handle = (C.c_char * 64)()
+        _lib.check(self.L.drl_comm_alloc(nbytes, C.byref(self.own), handle))
+        handles = [None] * world
+        td.all_gather_object(handles, bytes(handle))
+        self.opened = []
+        peers = (C.c_void_p * 8)()
+        for r in range(world):
+            if r == rank:
+                peers[r] = self.own.value
+            else:
+                p = C.c_void_p()
+                buf = (C.c_char * 64).from_buffer_copy(handles[r])
+                _lib.check(self.L.drl_comm_open(buf, C.byref(p)))
+                peers[r] = p.value
+                self.opened.append(p)
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.struct = _lib.CommT(world, rank, peers, 0, self.error_flag.data_ptr())
+        self.seq = 0
+        td.barrier()
+
+    def next(self):
+        """The drl_comm_t for the next minibatch step (sequence number advanced identically on every rank)."""
+        self.seq += 1
+        self.struct.seq = self.seq
+        return self.struct
+
+    def close(self):
+        from . import _lib
+        torch.cuda.synchronize()
+        td.barrier()
+        for p in self.opened:
+            self.L.drl_comm_close(p)
+        self.opened = []
+        if self.own:
+            self.L.drl_comm_free(self.own)
+            self.own = None
+
+
 def shutdown() -> None:
     if td.is_initialized():
         td.destroy_process_group()

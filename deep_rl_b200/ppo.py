@@ -51,6 +51,8 @@ class PPOConfig:
     anneal_lr: bool = True
     rollout_precision: str = "auto"  # "bf16": tcgen05 rollout (128 envs per CTA); "fp32": CUDA-core rollout; "auto": bf16 when
                                      # the update is bf16 and there are enough envs to fill the GPU with 128-env CTAs
+    grad_allreduce: str = "peer"     # multi-GPU gradient exchange: "peer" = one-shot all-reduce over NVLink peer memory inside
+                                     # the gradient kernel (bf16 update only), "nccl" = NCCL all-reduce between kernels
     update_precision: str = "bf16"   # "bf16": tcgen05 tensor-core update (bf16 operands, fp32 accumulate); "fp32": CUDA-core update
 
     @property
@@ -147,6 +149,9 @@ class PPOTrainer:
         self.env.reset()           # ppo.py:101
         self.kernel_launches = 0
         self.fused_step = True     # single GPU: fold + clip + Adam in one cooperative kernel after the gradient kernel
+        self.peer = None
+        if self.world > 1 and cfg.grad_allreduce == "peer" and self.grad_flags == 1:
+            self.peer = _dist.PeerComm(self.net, self.rank, self.world, dev)
         self.timing = False        # record CUDA events around each phase (bench.py)
         self.phase_events: Dict[str, list] = {}
 
@@ -206,6 +211,18 @@ class PPOTrainer:
                 start = k * M
                 count = min(M, B - start)
                 row = epoch * self.n_mb + k
+                if self.peer is not None:
+                    self.adam_step += 1
+                    with _Phase(self, "minibatch_grad"):    # gradient + fold + NVLink all-reduce + clip + Adam: one launch
+                        _lib.check(self.L.drl_ppo_minibatch_update_dist(
+                            net, self.agent.packed.data_ptr(), self.records.data_ptr(), self.idx.data_ptr(), start, count,
+                            self.adv_stats.data_ptr() + 8 * k, C.byref(self.coef), self.agent.flat_params.data_ptr(),
+                            self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.adam_step, lr,
+                            0.9, 0.999, 1e-5, cfg.max_grad_norm, self.loss_terms.data_ptr() + 32 * row,
+                            self.grad_norm.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, self.grad_flags,
+                            C.byref(self.peer.next()), st))
+                    self.kernel_launches += 1
+                    continue
                 if self.world == 1 and self.fused_step:
                     self.adam_step += 1
                     with _Phase(self, "minibatch_grad"):    # gradient kernel + fused fold/clip/Adam kernel
@@ -215,7 +232,7 @@ class PPOTrainer:
                             self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.adam_step, lr,
                             0.9, 0.999, 1e-5, cfg.max_grad_norm, self.loss_terms.data_ptr() + 32 * row,
                             self.grad_norm.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, self.grad_flags, st))
-                    self.kernel_launches += 2
+                    self.kernel_launches += 1 if self.grad_flags == 1 else 2
                     continue
                 with _Phase(self, "minibatch_grad"):
                     _lib.check(self.L.drl_ppo_minibatch_grad(
@@ -250,6 +267,8 @@ class PPOTrainer:
         self._h_terms.copy_(self._d_terms_src(), non_blocking=True)
         n, sum_ret, sum_len, entries = self.env.log.drain(with_entries=with_episode_log)
         lt = self._h_terms.tolist()
+        if self.peer is not None and int(self.peer.error_flag.item()) != 0:
+            raise _lib.DrlError("a peer rank did not arrive at the in-kernel all-reduce within the timeout")
         return {"loss": lt[0], "pg_loss": lt[1], "v_loss": lt[2], "entropy": lt[3], "approx_kl": lt[4],
                 "clipfrac": lt[5], "grad_norm": lt[8], "episodes": n,
                 "mean_return": (sum_ret / n) if n else float("nan"), "mean_length": (sum_len / n) if n else float("nan"),

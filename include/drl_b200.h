@@ -147,6 +147,23 @@ int drl_ppo_minibatch_grad(const drl_net_t* net, const float* packed, const floa
                            const drl_ppo_coef_t* coef, float* grad_out, float* loss_terms_out,
                            void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
+/* ---- peer-memory communicator for the fused multi-GPU minibatch step (one node, NVLink / NVSwitch) ----
+ * Each rank owns one symmetric buffer (drl_comm_bytes() bytes, allocated by drl_comm_alloc -- the one place the
+ * library allocates, because the memory must be exportable with cudaIpcGetMemHandle) and maps every peer's buffer
+ * with drl_comm_open.  The buffer holds two generations of the rank's folded gradient and arrival flags. */
+#define DRL_MAX_RANKS 8
+typedef struct {
+    int32_t  world, rank;
+    void*    peer[DRL_MAX_RANKS];   /* peer[r] = rank r's symmetric buffer as mapped in THIS process (peer[rank] = own) */
+    uint32_t seq;                   /* 1-based sequence number of this minibatch step, identical on all ranks */
+    int32_t* error_flag;            /* [1] device int, set to 1 if a peer did not arrive within the timeout */
+} drl_comm_t;
+size_t drl_comm_bytes(const drl_net_t* net);
+int drl_comm_alloc(size_t bytes, void** dev_ptr_out, void* ipc_handle_out /* 64 bytes */);
+int drl_comm_open(const void* ipc_handle /* 64 bytes */, void** peer_ptr_out);
+int drl_comm_close(void* peer_ptr);
+int drl_comm_free(void* dev_ptr);
+
 /* ---- single-GPU fusion of the three calls above/below: minibatch gradient, then ONE cooperative kernel that folds
  * the per-CTA partial gradients, clips by the global norm and applies Adam (ppo.py:159-192 in two launches).
  * `packed` is read by the gradient kernels and refreshed by the Adam step; grad_out receives the pre-clip gradient. */
@@ -155,6 +172,15 @@ int drl_ppo_minibatch_update(const drl_net_t* net, float* packed, const float* r
                              float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
                              double max_grad_norm, float* loss_terms_out, float* norm_out, void* workspace, size_t workspace_bytes,
                              uint32_t flags, void* stream);
+/* Multi-GPU form (tensor-core path only): the same single cooperative launch; between the local fold and the clip the
+ * CTAs publish their gradient slices in the symmetric buffer, wait for every peer's arrival flag and sum the peers'
+ * slices over NVLink in rank order (a one-shot all-reduce inside the kernel, identical result on every rank), then
+ * clip and apply Adam on gradient / world.  grad_out receives the summed gradient. */
+int drl_ppo_minibatch_update_dist(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
+                                  uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params,
+                                  float* grad_out, float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1,
+                                  double beta2, double eps, double max_grad_norm, float* loss_terms_out, float* norm_out,
+                                  void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm, void* stream);
 
 /* ---- clip_grad_norm_ + Adam, ppo.py:191-192 (after the gradient all-reduce) ----
  * grad is multiplied by grad_scale (1/world) first; `step` is the 1-based Adam step of this call.
