@@ -157,10 +157,11 @@ def run_b200(args):
                 if (envs == 65_536 and T == 128 and args.env_id == "CartPole-v1") else f"custom: {args.env_id}, {envs} envs/GPU x {T} steps")
     total_updates = args.warmup + 2 * args.steps + 8
     cfg = PPOConfig(env_id=args.env_id, num_envs=envs, num_steps=T, total_timesteps=envs * T * world * total_updates, seed=1,
-                    update_precision=args.precision)
+                    update_precision=args.precision, grad_allreduce=args.grad_allreduce)
     tr = PPOTrainer(cfg, rank=rank, world=world, device=dev)
     nu = cfg.num_updates(world)
     n_mb = tr.n_mb
+    tr_peer = tr.peer is not None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     for _ in range(max(3, args.warmup)):
@@ -261,6 +262,8 @@ def run_b200(args):
                        "value": 65_536 * T / (ms3 * 1e-3), "unit": "env-steps/s", "ms_per_step": ms3, "steps": 5}
         del tr3
 
+    if world > 1 and tr_peer:
+        tr.peer.close()
     if rank != 0:
         dist.shutdown()
         return
@@ -281,7 +284,8 @@ def run_b200(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tc else "f32", "data": "synthetic",
         "config": {"workload": workload, "precision": ("update GEMMs bf16 x bf16 -> fp32 on tcgen05; rollout, env, GAE, loss, Adam fp32/fp64" if tc else "fp32"), "env_id": args.env_id, "envs_per_gpu": envs, "num_steps": T, "hidden": 64,
                    "minibatch_size": M, "update_epochs": cfg.update_epochs, "optimizer_steps_per_update": cfg.update_epochs * n_mb,
-                   "parallelism": f"env-sharded x{world}", "l2": "flushed between updates (256 MiB memset outside the timed events); "
+                   "parallelism": f"env-sharded x{world}" + ("" if world == 1 else (", gradient all-reduce inside the gradient kernel over NVLink peer memory"
+                                                                                  if tr_peer else ", NCCL gradient all-reduce per minibatch")), "l2": "flushed between updates (256 MiB memset outside the timed events); "
                    "every update regenerates its own rollout data"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / args.steps,
                 "note": "public API PPOTrainer.update()+metrics() with a host sync and a device->host read of the loss terms, "
@@ -307,6 +311,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scaling-reference", action="store_true")
+    ap.add_argument("--grad-allreduce", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU gradient exchange: in-kernel NVLink peer-memory all-reduce, or NCCL between kernels")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="update GEMMs: bf16 = tcgen05 tensor cores (bf16 operands, fp32 accumulate), fp32 = CUDA cores")
     args = ap.parse_args()
