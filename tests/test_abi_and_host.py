@@ -147,7 +147,7 @@ t = torch.tensor(p1); dist.all_reduce_sum(t)
 np.testing.assert_allclose(t.numpy() / world, p1, rtol=0, atol=1e-7)     # ranks stay in lock-step
 assert dist.all_reduce_max(float(rank), "cpu") == 1.0
 dist.barrier(); dist.shutdown()
-print("rank", rank, "ok")
+sys.stdout.write(f"rank-{rank}-ok\n"); sys.stdout.flush()
 """
 
 
@@ -162,4 +162,4 @@ def test_gloo_world2_gradient_allreduce(tmp_path):
            "--master-port", str(port), str(script)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
-    assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
+    assert "rank-0-ok" in res.stdout and "rank-1-ok" in res.stdout
