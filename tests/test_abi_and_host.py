@@ -147,7 +147,7 @@ t = torch.tensor(p1); dist.all_reduce_sum(t)
 np.testing.assert_allclose(t.numpy() / world, p1, rtol=0, atol=1e-7)     # ranks stay in lock-step
 assert dist.all_reduce_max(float(rank), "cpu") == 1.0
 dist.barrier(); dist.shutdown()
-sys.stdout.write(f"rank-{rank}-ok\n"); sys.stdout.flush()
+sys.stdout.write("rank-%d-ok\n" % rank); sys.stdout.flush()
 """
 
 
