@@ -39,9 +39,10 @@ struct TcSmem {
     static constexpr int OFF_H1 = (OFF_W + W_BYTES + 1023) / 1024 * 1024;   // two buffers x (actor, critic) x 16 KB
     static constexpr int OFF_H2 = OFF_H1 + 65536;
     static constexpr int OFF_DZ = OFF_H2 + 32768;
-    static constexpr int OFF_OBS = OFF_DZ + 32768;     // three NS16 buffers [obs_hi|1|obs_lo] (tile % 3)
+    static constexpr int OFF_DZ1 = OFF_DZ + 32768;     // dz1 has its own tile: the dz2 readers (dW2, db2) may still be running
+    static constexpr int OFF_OBS = OFF_DZ1 + 32768;    // three NS16 buffers [obs_hi|1|obs_lo] (tile % 3)
     static constexpr int OFF_DOUT = OFF_OBS + 12288;   // one NS16 buffer
-    static constexpr int OFF_BAR = OFF_DOUT + 4096;    // 5 mbarriers + TMEM slot
+    static constexpr int OFF_BAR = OFF_DOUT + 4096;    // 6 mbarriers + TMEM slot
     static constexpr int OFF_XCH = OFF_BAR + 64;       // head partial sums [net][half][A][128 rows] fp32
     static constexpr int OFF_RED = OFF_XCH + 2 * 2 * 4 * 128 * 4;
     static constexpr int TOTAL = OFF_RED + 16 * 12 * 4 + 1024;   // + alignment slack
@@ -103,10 +104,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     unsigned char* tH1 = sm + S::OFF_H1;
     unsigned char* tH2 = sm + S::OFF_H2;
     unsigned char* tDZ = sm + S::OFF_DZ;
+    unsigned char* tDZ1 = sm + S::OFF_DZ1;
     unsigned char* tOBS = sm + S::OFF_OBS;
     unsigned char* tDOUT = sm + S::OFF_DOUT;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd, 2 bwd, 3 w1, 4 layer 1
-    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd, 2 dh1, 3 w1, 4 layer 1, 5 dW2/db2/dW4
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 6);
     float* xch = reinterpret_cast<float*>(sm + S::OFF_XCH);
     float* red = reinterpret_cast<float*>(sm + S::OFF_RED);
 
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     // ---- prologue: barriers, TMEM, weights by TMA bulk copy ----
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 6; ++i) mbar_init(bars + i, 1);
         mbar_fence_init();
     }
     if (warp == 1) umma::tmem_alloc(slot, TC_COLS);
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     if (is_mma_warp) {
         // =========================== MMA-issuer warp ===========================
         const uint32_t aW2 = smem_u32(tW2), aH1 = smem_u32(tH1), aH2 = smem_u32(tH2), aDZ = smem_u32(tDZ);
-        const uint32_t aOBS = smem_u32(tOBS), aDOUT = smem_u32(tDOUT);
+        const uint32_t aOBS = smem_u32(tOBS), aDOUT = smem_u32(tDOUT), aDZ1 = smem_u32(tDZ1);
         constexpr uint32_t ID_FWD = umma::make_idesc(128, 64, false, false);
         constexpr uint32_t ID_DH1 = umma::make_idesc(128, 64, false, true);
         constexpr uint32_t ID_W2 = umma::make_idesc(128, 128, true, true);
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                     for (int kb = 0; kb < 4; ++kb)
                         umma::mma(tmem + C_DH + n2 * 64, umma::make_desc(aDZ + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
                                   umma::make_desc(aW2 + n2 * 8192 + kb * 2048, 8192, 1024, umma::LAYOUT_SW128), ID_DH1, kb > 0);
+                umma::commit(bars + 2);          // dh1 is all that Z(k) waits for
 #pragma unroll
                 for (int kb = 0; kb < 8; ++kb)
                     umma::mma(tmem + C_W2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                 for (int kb = 0; kb < 8; ++kb)
                     umma::mma(tmem + C_W4, umma::make_desc(aH2 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
                               umma::make_desc(aDOUT + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
-                umma::commit(bars + 2);
+                umma::commit(bars + 5);          // weight-gradient GEMMs: only gate the reuse of their operand tiles
             }
             __syncwarp();
             TC_STAMP(1);
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
             if (umma::elect_one()) {
 #pragma unroll
                 for (int kb = 0; kb < 8; ++kb)
-                    umma::mma(tmem + C_W1, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                    umma::mma(tmem + C_W1, umma::make_desc(aDZ1 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
                               umma::make_desc(obsb + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
                 umma::commit(bars + 3);
             }
@@ -294,6 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         // ================= X(k): heads, loss, output gradients, dz2 =================
         TC_STAMP(0);
         mbar_wait(bars + 1, par);
+        if (k > 0) mbar_wait(bars + 5, (k - 1) & 1u);   // dW2/db2/dW4(k-1) have finished reading the h2, dz2, dout, h1 tiles
         umma::fence_after_sync();
         TC_STAMP(1);
         {
@@ -429,7 +433,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                 for (int j = 0; j < 4; ++j) h[4 * k4 + j] = dh[j] * fmaf(-h[4 * k4 + j], h[4 * k4 + j], 1.0f);
             }
             TC_STAMP(4);
-            if (k > 0) mbar_wait(bars + 3, (k - 1) & 1u);   // w1(k-1) has finished reading tDZ
             TC_STAMP(5);
             store_half_row_sw128(tDZ + net * 16384, r, half * 4, h);
         }
@@ -448,18 +451,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
 
         // ================= Z(k): dz1 = dh1 * (1 - h1^2) (hides fwd(k+1)) =================
         TC_STAMP(7);
-        mbar_wait(bars + 2, par);
-        umma::fence_after_sync();
-        TC_STAMP(8);
         {
+            const unsigned char* h1row = tH1 + par * 32768 + net * 16384;
+            uint4 hq[4];                                   // this thread's h1 values (bf16): loaded before the wait
+#pragma unroll
+            for (int c = 0; c < 4; ++c) hq[c] = *reinterpret_cast<const uint4*>(h1row + umma::sw128_off(r, half * 4 + c));
+            mbar_wait(bars + 2, par);
+            if (k > 0) mbar_wait(bars + 3, (k - 1) & 1u);   // w1(k-1) has finished reading tDZ1
+            umma::fence_after_sync();
+            TC_STAMP(8);
             float dh[HU];
             umma::ld32(trow + C_DH + net * 64 + u0, dh);
-            const unsigned char* h1row = tH1 + par * 32768 + net * 16384;
-            unsigned char* dzrow = tDZ + net * 16384;
+            unsigned char* dzrow = tDZ1 + net * 16384;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {   // 16-byte chunk at a time: h1 (bf16) in, dz1 (bf16) out
-                const uint32_t off = umma::sw128_off(r, half * 4 + c);
-                const uint4 q = *reinterpret_cast<const uint4*>(h1row + off);
+                const uint4 q = hq[c];
                 const float hv[8] = {umma::bf16_lo(q.x), umma::bf16_hi(q.x), umma::bf16_lo(q.y), umma::bf16_hi(q.y),
                                      umma::bf16_lo(q.z), umma::bf16_hi(q.z), umma::bf16_lo(q.w), umma::bf16_hi(q.w)};
                 float z[8];
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                 uint4 o4;
                 o4.x = umma::pack_bf16(z[0], z[1]); o4.y = umma::pack_bf16(z[2], z[3]);
                 o4.z = umma::pack_bf16(z[4], z[5]); o4.w = umma::pack_bf16(z[6], z[7]);
-                *reinterpret_cast<uint4*>(dzrow + off) = o4;
+                *reinterpret_cast<uint4*>(dzrow + umma::sw128_off(r, half * 4 + c)) = o4;
             }
         }
         umma::fence_proxy_async();
@@ -477,6 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         TC_STAMP(9);
     }
     mbar_wait(bars + 3, (nmy - 1) & 1u);
+    mbar_wait(bars + 5, (nmy - 1) & 1u);
     umma::fence_after_sync();
 
     // ================= epilogue: this CTA's partial gradient, canonical layout =================
