@@ -38,7 +38,8 @@ struct RoTcSmem {
 
 template <int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env, const float* __restrict__ packed, int T,
-                                                                   uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log) {
+                                                                   uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log,
+                                                                   int rows) {
     using SP = EnvSpec<KIND>;
     constexpr int O = SP::O, A = SP::A, OP = SP::OP;
     using P = Packed<O, A>;
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
         mbar_init(bars + 1, 1);
         mbar_fence_init();
     }
-    if (warp == 1) umma::tmem_alloc(slot, 128);
+    if (is_mma_warp) umma::tmem_alloc(slot, 128);      // the issuer warp always stays: it also frees the columns
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -81,12 +82,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
     }
     const uint32_t tmem = *slot;
     mbar_wait(bars, 0);
+    // `rows` (32, 64 or 128) environments per CTA: with few environments the per-step latency, not the throughput, sets
+    // the pace, so they are spread over more CTAs and the warps of the unused row windows leave.
+    const uint32_t nthr = (uint32_t)(rows / 32) * 4u * 32u + 32u;      // participants of the issuer hand-off barrier
+    if (!is_mma_warp && (warp & 3) * 32 >= rows) return;
 
     if (is_mma_warp) {
         const uint32_t aW2 = smem_u32(tW2), aH1 = smem_u32(tH1);
         constexpr uint32_t ID_FWD = umma::make_idesc(128, 64, false, false);
         for (int t = 0; t <= T; ++t) {
-            named_bar_sync(RB_FWD, TC_THREADS);
+            named_bar_sync(RB_FWD, nthr);
             umma::fence_after_sync();
             if (umma::elect_one()) {
 #pragma unroll
@@ -101,6 +106,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
         }
         umma::fence_before_sync();
         __syncthreads();
+        umma::tmem_dealloc(tmem, 128);
         return;
     }
 
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
     const int nheads = net == 0 ? A : 1;
     const bool owner_warp = warp < 4;                         // actor, first half: owns the env state
     const int N = env.num_envs;
-    const int n = blockIdx.x * TC_TILE + r;
+    const int n = blockIdx.x * rows + r;
     const bool own = owner_warp && n < N;
     const uint32_t gid = env.env_gid0 + (uint32_t)n;
 
@@ -170,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
-        named_bar_arrive(RB_FWD, TC_THREADS);
+        named_bar_arrive(RB_FWD, nthr);
 
         // ---- S2: layer-2 epilogue and partial head dot products ----
         mbar_wait(bars + 1, (uint32_t)t & 1u);
@@ -233,7 +239,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
     if (own) env_store(e, env, n);
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tmem, 128);
 }
 
 template <int KIND>
@@ -242,8 +247,15 @@ static int launch_rollout_tc_kind(const drl_env_t& env, const float* packed, int
     using SP = EnvSpec<KIND>;
     const int smem = RoTcSmem<SP::O, SP::A>::TOTAL;
     DRL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int blocks = (env.num_envs + TC_TILE - 1) / TC_TILE;
-    rollout_tc_kernel<KIND><<<blocks, TC_THREADS, smem, st>>>(env, packed, T, step0, buf, log);
+    // envs per CTA: 128 when that fills the GPU, otherwise fewer rows per CTA over more CTAs (latency-bound regime)
+    const int sms = sm_count();
+    int rows = 128;
+    if ((env.num_envs + 127) / 128 < sms) rows = (env.num_envs + 63) / 64 <= sms ? 64 : 128;
+    if ((env.num_envs + 63) / 64 < sms && (env.num_envs + 31) / 32 <= sms) rows = 32;
+    const char* ov = getenv("DRL_ROLLOUT_ROWS");
+    if (ov) { const int v = atoi(ov); if (v == 32 || v == 64 || v == 128) rows = v; }
+    const int blocks = (env.num_envs + rows - 1) / rows;
+    rollout_tc_kernel<KIND><<<blocks, TC_THREADS, smem, st>>>(env, packed, T, step0, buf, log, rows);
     DRL_LAUNCH_CHECK("rollout_tc_kernel");
     return DRL_OK;
 }

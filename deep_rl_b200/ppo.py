@@ -49,8 +49,8 @@ class PPOConfig:
     hidden: int = 64
     num_minibatches: int = 4     # reference: minibatch_size = num_steps // 4
     anneal_lr: bool = True
-    rollout_precision: str = "auto"  # "bf16": tcgen05 rollout (128 envs per CTA); "fp32": CUDA-core rollout; "auto": bf16 when
-                                     # the update is bf16 and there are enough envs to fill the GPU with 128-env CTAs
+    rollout_precision: str = "auto"  # "bf16": tcgen05 rollout (32-128 envs per CTA); "fp32": CUDA-core rollout; "auto": bf16 when
+                                     # the update is bf16 and there are at least 2048 envs
     grad_allreduce: str = "peer"     # multi-GPU gradient exchange: "peer" = one-shot all-reduce over NVLink peer memory inside
                                      # the gradient kernel (bf16 update only), "nccl" = NCCL all-reduce between kernels
     update_precision: str = "bf16"   # "bf16": tcgen05 tensor-core update (bf16 operands, fp32 accumulate); "fp32": CUDA-core update
@@ -141,7 +141,7 @@ class PPOTrainer:
         if cfg.rollout_precision not in ("auto", "bf16", "fp32"):
             raise ValueError(f"rollout_precision={cfg.rollout_precision!r}")
         tc_rollout = cfg.rollout_precision == "bf16" or (cfg.rollout_precision == "auto" and cfg.update_precision == "bf16"
-                                                         and N >= 128 * 128)
+                                                         and N >= 2048)
         self.rollout_flags = 1 if tc_rollout else 0
         self.adam_step = 0
         self.update_idx = 0

@@ -99,6 +99,16 @@ def test_tensor_core_rollout_vs_oracle(env_id, N, T):
     _check_rollout(env_id, N, T, seed=3, tc=True)
 
 
+@pytest.mark.parametrize("rows", [32, 64, 128])
+def test_tensor_core_rollout_rows_per_cta(rows):
+    """Few envs spread over more CTAs (32 / 64 rows of the 128-row tile used): same results as the oracle."""
+    os.environ["DRL_ROLLOUT_ROWS"] = str(rows)
+    try:
+        _check_rollout("CartPole-v1", 200, 20, seed=5, tc=True, rounds=1)
+    finally:
+        os.environ.pop("DRL_ROLLOUT_ROWS", None)
+
+
 def test_rollout_world_size_invariance():
     """Global env id feeds the Philox counter: rank 1 of a 2-rank job reproduces envs [N, 2N) of a 1-rank job."""
     import deep_rl_b200 as drl
