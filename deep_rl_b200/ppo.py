@@ -150,7 +150,8 @@ class PPOTrainer:
         self.kernel_launches = 0
         self.fused_step = True     # single GPU: fold + clip + Adam in one cooperative kernel after the gradient kernel
         self.peer = None
-        if self.world > 1 and cfg.grad_allreduce == "peer" and self.grad_flags == 1:
+        if (self.world > 1 and cfg.grad_allreduce == "peer" and self.grad_flags == 1
+                and torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.peer = _dist.PeerComm(self.net, self.rank, self.world, dev)
         self.timing = False        # record CUDA events around each phase (bench.py)
         self.phase_events: Dict[str, list] = {}
