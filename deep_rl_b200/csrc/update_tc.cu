@@ -2,7 +2,7 @@
 // deep_rl/ppo.py:159-190.  Same inputs, outputs and per-CTA partial-gradient format as ppo_grad_kernel
 // (update_ops.cu); operands of the GEMMs are bf16, accumulation is fp32 in tensor memory.
 //
-// One persistent CTA per SM: 16 compute warps + 1 MMA-issuer warp.  A tile is 128 samples = the 128 TMEM lanes;
+// One persistent CTA per SM: 16 compute warps + 1 MMA-issuer warp + 1 loader warp.  A tile is 128 samples = the 128 TMEM lanes;
 // compute thread (warp w, lane l) owns sample row r = 32*(w&3)+l, net (w>>3) (0 = actor trunk, 1 = critic trunk) and
 // hidden units [32*((w>>2)&1), +32) of that net, i.e. four threads share a row.  Work per tile k:
 //   P0(k)  layer 1 on CUDA cores from the prefetched 32-byte record (K = 4/6 is degenerate for UMMA),
@@ -19,9 +19,13 @@
 // handed over, and no CTA-wide barrier sits in the loop:
 //   X(k): wait fwd(k), P1(k), hand bwd(k)   Y(k): P0(k+1), hand fwd(k+1)   Z(k): wait bwd(k), P2(k), hand w1(k)
 // "hand" = fence.proxy.async + bar.arrive on a named barrier; the issuer warp bar.syncs on it, issues the
-// tcgen05.mma group and commits to an mbarrier the compute warps wait on.  h1 and [obs|1] tiles are double-buffered,
-// z2 and dh1 have separate TMEM columns, records are prefetched one tile ahead and their indices two tiles ahead.  All weight-gradient accumulators live in TMEM for the whole kernel (432 of 512 columns used) and
-// are written once, as this CTA's partial gradient, at the end.
+// tcgen05.mma group and commits to an mbarrier the compute warps wait on.  h1 tiles are double-buffered, z2 and dh1
+// have separate TMEM columns.  The gather is decoupled from the compute warps: the loader warp reads the permuted
+// indices and the 32/64-byte records of tile k+2 (plain global loads; their latency and their scoreboards stay in that
+// warp), writes the [obs_hi|1|obs_lo] operand tile and the per-row scalars {logp, adv, val, act} into a three-deep
+// shared-memory ring and signals a "full" mbarrier; the slot is handed back by a tcgen05.commit after the last GEMM that
+// reads it.  All weight-gradient accumulators live in TMEM for the whole kernel (432 of 512 columns used) and are
+// written once, as this CTA's partial gradient, at the end.
 #include "drl_pack.cuh"
 #include "drl_tc_common.cuh"
 #include "drl_update.cuh"
@@ -42,24 +46,24 @@ struct TcSmem {
     static constexpr int OFF_DZ1 = OFF_DZ + 32768;     // dz1 has its own tile: the dz2 readers (dW2, db2) may still be running
     static constexpr int OFF_OBS = OFF_DZ1 + 32768;    // three NS16 buffers [obs_hi|1|obs_lo] (tile % 3)
     static constexpr int OFF_DOUT = OFF_OBS + 12288;   // one NS16 buffer
-    static constexpr int OFF_BAR = OFF_DOUT + 4096;    // 6 mbarriers + TMEM slot
-    static constexpr int OFF_XCH = OFF_BAR + 64;       // head partial sums [net][half][A][128 rows] fp32
+    static constexpr int OFF_SCAL = OFF_DOUT + 4096;   // three buffers of per-row scalars {logp_old, adv, val_old, act} (16 B each)
+    static constexpr int OFF_BAR = OFF_SCAL + 3 * 2048;   // 12 mbarriers + TMEM slot
+    static constexpr int OFF_XCH = OFF_BAR + 128;      // head partial sums [net][half][A][128 rows] fp32
     static constexpr int OFF_RED = OFF_XCH + 2 * 2 * 4 * 128 * 4;
     static constexpr int TOTAL = OFF_RED + 16 * 12 * 4 + 1024;   // + alignment slack
+    static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
 // diagnostics: cycle stamps of CTA 0 (slot = tile * 16 + event), enabled with DRL_TC_DEBUG=1
 #define TC_STAMP(ev) do { if (g.dbg != nullptr && blockIdx.x == 0 && lane == 0 && k < 12) g.dbg[(warp == 0 ? 0 : 256) + k * 16 + (ev)] = clock64(); } while (0)
 
+// whole-kernel stamps of CTA 0 (thread 0): slots 8..15 of the issuer rows of the debug block
+#define TC_KSTAMP(n) do { if (g.dbg != nullptr && blockIdx.x == 0 && tid == 0) g.dbg[256 + ((n) >> 3) * 16 + 8 + ((n) & 7)] = clock64(); } while (0)
+
 enum : uint32_t { BAR_FWD = 1, BAR_BWD = 2, BAR_W1 = 3, BAR_PAIR0 = 4, BAR_L1 = 12 };   // named barriers (0 = __syncthreads)
 
-template <int OW>
-struct TcRecord {       // one sample record, held in registers between its prefetch and its use
-    float x[OW];
-    float logp_old, adv, val_old;
-    int act;
-    bool valid;
-};
+constexpr int GRAD_TC_BLOCK = TC_THREADS + 32;   // + the loader warp
+constexpr int RING = 3;                          // depth of the [obs|1] / scalar ring
 
 // sample id of row r of this CTA's tile `tile` (0xFFFFFFFF = padding row)
 __device__ __forceinline__ uint32_t tc_sample_index(const GradArgs& g, uint32_t tile, uint32_t ntiles, int r) {
@@ -69,26 +73,8 @@ __device__ __forceinline__ uint32_t tc_sample_index(const GradArgs& g, uint32_t 
     return g.idx ? __ldg(g.idx + i) : i;
 }
 
-template <int OW, int OP, int RW>
-__device__ __forceinline__ void tc_load_record(TcRecord<OW>& rc, const GradArgs& g, uint32_t s) {
-#pragma unroll
-    for (int i = 0; i < OW; ++i) rc.x[i] = 0.0f;
-    rc.logp_old = 0.f; rc.adv = 0.f; rc.val_old = 0.f; rc.act = 0;
-    rc.valid = s != 0xFFFFFFFFu;
-    if (rc.valid) {
-        const float4* r4 = reinterpret_cast<const float4*>(g.rec + (size_t)s * RW);
-#pragma unroll
-        for (int q = 0; q < OP / 4; ++q) {
-            const float4 v4 = __ldg(r4 + q);
-            rc.x[4 * q] = v4.x; rc.x[4 * q + 1] = v4.y; rc.x[4 * q + 2] = v4.z; rc.x[4 * q + 3] = v4.w;
-        }
-        const float4 t4 = __ldg(r4 + RW / 4 - 1);
-        rc.logp_old = t4.x; rc.adv = t4.y; rc.val_old = t4.z; rc.act = __float_as_int(t4.w);
-    }
-}
-
 template <int O, int A, int OP, int RW>
-__global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) {
+__global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs g) {
     using P = Packed<O, A>;
     using S = TcSmem<O, A>;
     constexpr int OW = P::OW;
@@ -107,13 +93,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     unsigned char* tDZ1 = sm + S::OFF_DZ1;
     unsigned char* tOBS = sm + S::OFF_OBS;
     unsigned char* tDOUT = sm + S::OFF_DOUT;
+    uint4* sSCAL = reinterpret_cast<uint4*>(sm + S::OFF_SCAL);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd, 2 dh1, 3 w1, 4 layer 1, 5 dW2/db2/dW4
-    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* ring_full = bars + 6;                                  // loader -> consumers, one per ring slot (32 arrivals)
+    uint64_t* ring_empty = bars + 6 + RING;                          // tcgen05.commit after the last GEMM reading the slot
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * RING);
     float* xch = reinterpret_cast<float*>(sm + S::OFF_XCH);
     float* red = reinterpret_cast<float*>(sm + S::OFF_RED);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool is_mma_warp = warp == TC_COMPUTE / 32;
+    const bool is_loader_warp = warp == TC_COMPUTE / 32 + 1;
     const int rw = warp & 3, half = (warp >> 2) & 1, net = (warp >> 3) & 1;
     const int r = rw * 32 + lane;
     const int u0 = half * HU;
@@ -121,9 +111,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     const uint32_t nmy = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles of this CTA (>= 1)
 
     // ---- prologue: barriers, TMEM, weights by TMA bulk copy ----
+    TC_KSTAMP(0);
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) mbar_init(bars + i, 1);
+#pragma unroll
+        for (int i = 0; i < RING; ++i) { mbar_init(ring_full + i, 32); mbar_init(ring_empty + i, 1); }
         mbar_fence_init();
     }
     if (warp == 1) umma::tmem_alloc(slot, TC_COLS);
@@ -140,6 +133,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     }
     const uint32_t tmem = *slot;
 
+    if (is_loader_warp) {
+        // =========================== loader warp ===========================
+        // lane l owns rows l, l+32, l+64, l+96 of every tile.  Indices are fetched one tile ahead of the records.
+        uint32_t sidx[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sidx[q] = tc_sample_index(g, blockIdx.x, ntiles, lane + 32 * q);
+        uint32_t b = 0, use_par = 0;
+        for (uint32_t j = 0; j < nmy; ++j) {
+            float4 rv[4][OP / 4 + 1];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int c = 0; c <= OP / 4; ++c) rv[q][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rv[q][OP / 4].w = __int_as_float(-1);                  // act < 0 marks a padding row
+                if (sidx[q] != 0xFFFFFFFFu) {
+                    const float4* r4 = reinterpret_cast<const float4*>(g.rec + (size_t)sidx[q] * RW);
+#pragma unroll
+                    for (int c = 0; c < OP / 4; ++c) rv[q][c] = __ldg(r4 + c);
+                    rv[q][OP / 4] = __ldg(r4 + RW / 4 - 1);
+                }
+            }
+            if (j + 1 < nmy) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sidx[q] = tc_sample_index(g, blockIdx.x + (j + 1) * gridDim.x, ntiles, lane + 32 * q);
+            }
+            if (j >= RING) mbar_wait(ring_empty + b, use_par ^ 1u);    // the GEMMs of tile j - RING have released the slot
+            unsigned char* obst = tOBS + b * 4096;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int row = lane + 32 * q;
+                float o16[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o16[i] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < O; ++i) {       // obs = hi + lo to 16 mantissa bits
+                    const float4 v4 = rv[q][i / 4];
+                    const float x = (i & 3) == 0 ? v4.x : ((i & 3) == 1 ? v4.y : ((i & 3) == 2 ? v4.z : v4.w));
+                    const float hi = __bfloat162float(__float2bfloat16_rn(x));
+                    o16[i] = hi;
+                    o16[8 + i] = x - hi;
+                }
+                o16[O] = 1.0f;
+                umma::store_row_ns16(obst, TC_TILE, row, o16);
+                sSCAL[b * TC_TILE + row] = make_uint4(__float_as_uint(rv[q][OP / 4].x), __float_as_uint(rv[q][OP / 4].y),
+                                                      __float_as_uint(rv[q][OP / 4].z), __float_as_uint(rv[q][OP / 4].w));
+            }
+            umma::fence_proxy_async();
+            mbar_arrive(ring_full + b);
+            if (++b == RING) { b = 0; use_par ^= 1u; }
+        }
+        __syncthreads();           // epilogue barrier of the compute warps
+        return;
+    }
+
     if (is_mma_warp) {
         // =========================== MMA-issuer warp ===========================
         const uint32_t aW2 = smem_u32(tW2), aH1 = smem_u32(tH1), aH2 = smem_u32(tH2), aDZ = smem_u32(tDZ);
@@ -152,8 +199,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         const uint32_t aW1B = smem_u32(tW1B);
         constexpr uint32_t ID_L1 = umma::make_idesc(128, 64, false, false);
         // layer 1 of tile k: z1 = [obs_hi|1|obs_lo] . [W1|b1|W1]^T, K = 16, both operands K-major without swizzle
-        auto issue_l1 = [&](uint32_t k) {
-            const uint32_t obsb = aOBS + (k % 3u) * 4096;
+        auto issue_l1 = [&](uint32_t slot_b) {
+            const uint32_t obsb = aOBS + slot_b * 4096;
 #pragma unroll
             for (int n2 = 0; n2 < 2; ++n2)
                 umma::mma(tmem + C_ZF + n2 * 64, umma::make_desc(obsb, 2048, 128, umma::LAYOUT_NONE),
@@ -170,22 +217,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                               umma::make_desc(aW2 + n2 * 8192 + kb * 32, 16, 1024, umma::LAYOUT_SW128), ID_FWD, kb > 0);
             umma::commit(bars + 1);
         };
+        uint32_t bn = 0, bn_par = 0;      // ring slot / use parity of the NEXT tile to get its layer-1 GEMM
+        uint32_t bc = 0;                  // ring slot of the current tile
         named_bar_sync(BAR_L1, TC_THREADS);
+        mbar_wait(ring_full + bn, bn_par);
         umma::fence_after_sync();
-        if (umma::elect_one()) issue_l1(0);
+        if (umma::elect_one()) issue_l1(bn);
         __syncwarp();
+        if (++bn == RING) { bn = 0; bn_par ^= 1u; }
         named_bar_sync(BAR_FWD, TC_THREADS);
         umma::fence_after_sync();
         if (umma::elect_one()) issue_fwd(0);
         __syncwarp();
         for (uint32_t k = 0; k < nmy; ++k) {
             const uint32_t par = k & 1u, acc = k > 0 ? 1u : 0u;
-            const uint32_t obsb = aOBS + (k % 3u) * 4096;
+            const uint32_t obsb = aOBS + bc * 4096;
             if (k + 1 < nmy) {
-                named_bar_sync(BAR_L1, TC_THREADS);      // z2(k) consumed, obs tile of k+1 written
+                named_bar_sync(BAR_L1, TC_THREADS);      // z2(k) consumed
+                mbar_wait(ring_full + bn, bn_par);       // [obs|1] tile of k+1 written by the loader
                 umma::fence_after_sync();
-                if (umma::elect_one()) issue_l1(k + 1);
+                if (umma::elect_one()) issue_l1(bn);
                 __syncwarp();
+                if (++bn == RING) { bn = 0; bn_par ^= 1u; }
             }
             named_bar_sync(BAR_BWD, TC_THREADS);
             umma::fence_after_sync();
@@ -232,9 +285,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                     umma::mma(tmem + C_W1, umma::make_desc(aDZ1 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
                               umma::make_desc(obsb + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
                 umma::commit(bars + 3);
+                umma::commit(ring_empty + bc);   // last reader of ring slot bc (tile k) is done: the loader may refill it
             }
             __syncwarp();
             TC_STAMP(5);
+            if (++bc == RING) bc = 0;
         }
         umma::fence_before_sync();
         __syncthreads();           // epilogue barrier of the compute warps
@@ -250,26 +305,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
     float lsum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // pg, v, entropy, kl, clipfrac partial sums (half-0 threads only)
     float gb4[4] = {0.f, 0.f, 0.f, 0.f};         // head-bias gradients: actor slots 0..A-1, critic slot 3
 
-    TcRecord<OW> rec_cur, rec_next;
-    tc_load_record<OW, OP, RW>(rec_cur, g, tc_sample_index(g, blockIdx.x, ntiles, r));
-    uint32_t s_next = tc_sample_index(g, blockIdx.x + gridDim.x, ntiles, r);
+    TC_KSTAMP(1);
     mbar_wait(bars, 0);
+    TC_KSTAMP(2);
 
-    // owners (warps 0-3): row r of the [obs_hi | 1 | 0.. | obs_lo | 0..] tile of tile k -- A operand of the layer-1
-    // GEMM and B operand of the dW1/db1 and db2 GEMMs.  obs = hi + lo to 16 mantissa bits.
-    auto write_obs_tile = [&](const TcRecord<OW>& rc, uint32_t k) {
-        float o16[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o16[i] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < O; ++i) {
-            const float hi = __bfloat162float(__float2bfloat16_rn(rc.x[i]));
-            o16[i] = hi;
-            o16[8 + i] = rc.x[i] - hi;
-        }
-        o16[O] = 1.0f;
-        umma::store_row_ns16(tOBS + (k % 3u) * 4096, TC_TILE, r, o16);
-    };
     // layer-1 epilogue of tile k: z1 from TMEM -> tanh -> bf16 h1 tile (buffer k & 1), then hand fwd(k)
     auto phase0 = [&](uint32_t k) {
         mbar_wait(bars + 4, k & 1u);
@@ -284,12 +323,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         named_bar_arrive(BAR_FWD, TC_THREADS);
     };
 
-    if (warp < 4) write_obs_tile(rec_cur, 0);
-    umma::fence_proxy_async();
     named_bar_arrive(BAR_L1, TC_THREADS);
     phase0(0);
-    tc_load_record<OW, OP, RW>(rec_next, g, s_next);
-    s_next = tc_sample_index(g, blockIdx.x + 2 * gridDim.x, ntiles, r);
+    uint32_t rb = 0, rb_par = 0;          // ring slot / use parity of the current tile
+    TC_KSTAMP(3);
 
     for (uint32_t k = 0; k < nmy; ++k) {
         const uint32_t par = k & 1u;
@@ -304,8 +341,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
             float h[HU];
             umma::ld32(trow + C_ZF + net * 64 + u0, h);
             if (k + 1 < nmy) {   // z2(k) is in registers: the layer-1 GEMM of tile k+1 may overwrite its TMEM columns
-                if (warp < 4) write_obs_tile(rec_next, k + 1);
-                umma::fence_proxy_async();
                 umma::fence_before_sync();
                 named_bar_arrive(BAR_L1, TC_THREADS);
             }
@@ -356,7 +391,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
             float d[A];
 #pragma unroll
             for (int a = 0; a < A; ++a) d[a] = 0.0f;
-            if (rec_cur.valid) {
+            mbar_wait(ring_full + rb, rb_par);     // long complete: the loader runs two tiles ahead
+            const uint4 sc = sSCAL[rb * TC_TILE + r];
+            const float rc_logp_old = __uint_as_float(sc.x), rc_adv = __uint_as_float(sc.y), rc_val_old = __uint_as_float(sc.z);
+            const int rc_act = (int)sc.w;
+            if (rc_act >= 0) {
                 if (net == 0) {
                     float m = out[0];
 #pragma unroll
@@ -372,10 +411,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                         lp[a] = out[a] - lse;
                         p[a] = __expf(lp[a]);
                         ent -= p[a] * lp[a];
-                        if (a == rec_cur.act) new_logp = lp[a];
+                        if (a == rc_act) new_logp = lp[a];
                     }
-                    const float nadv = (rec_cur.adv - adv_mean) * adv_rstd;
-                    const float logratio = new_logp - rec_cur.logp_old;
+                    const float nadv = (rc_adv - adv_mean) * adv_rstd;
+                    const float logratio = new_logp - rc_logp_old;
                     const float ratio = __expf(logratio);
                     const float pg1 = -nadv * ratio;
                     const float pg2 = -nadv * fminf(fmaxf(ratio, 1.0f - g.clip_coef), 1.0f + g.clip_coef);
@@ -388,17 +427,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
                     }
 #pragma unroll
                     for (int a = 0; a < A; ++a) {
-                        const float onehot = a == rec_cur.act ? 1.0f : 0.0f;
+                        const float onehot = a == rc_act ? 1.0f : 0.0f;
                         d[a] = inv_m * (dpg * (onehot - p[a]) + g.ent_coef * p[a] * (lp[a] + ent));
                         if (half == 0) gb4[a] += d[a];
                     }
                 } else {
                     const float v = out[0];
-                    const float ret = rec_cur.adv + rec_cur.val_old;
+                    const float ret = rc_adv + rc_val_old;
                     const float vd = v - ret;
                     const float vu = vd * vd;
-                    const float vdiff = v - rec_cur.val_old;
-                    const float vc = rec_cur.val_old + fminf(fmaxf(vdiff, -g.clip_coef), g.clip_coef);
+                    const float vdiff = v - rc_val_old;
+                    const float vc = rc_val_old + fminf(fmaxf(vdiff, -g.clip_coef), g.clip_coef);
                     const float vcd = vc - ret;
                     const float vcl = vcd * vcd;
                     const float gcl = (vdiff >= -g.clip_coef && vdiff <= g.clip_coef) ? vcd : 0.0f;
@@ -444,9 +483,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         // ================= Y(k): layer 1 of the next tile, hand fwd(k+1) (hides bwd(k)) =================
         if (k + 1 < nmy) {
             phase0(k + 1);
-            rec_cur = rec_next;
-            tc_load_record<OW, OP, RW>(rec_next, g, s_next);
-            s_next = tc_sample_index(g, blockIdx.x + (k + 3) * gridDim.x, ntiles, r);
         }
 
         // ================= Z(k): dz1 = dh1 * (1 - h1^2) (hides fwd(k+1)) =================
@@ -481,10 +517,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         umma::fence_before_sync();
         named_bar_arrive(BAR_W1, TC_THREADS);
         TC_STAMP(9);
+        if (++rb == RING) { rb = 0; rb_par ^= 1u; }
     }
     mbar_wait(bars + 3, (nmy - 1) & 1u);
     mbar_wait(bars + 5, (nmy - 1) & 1u);
     umma::fence_after_sync();
+    TC_KSTAMP(4);
 
     // ================= epilogue: this CTA's partial gradient, canonical layout =================
     float* part = g.grad_part + (size_t)blockIdx.x * g.ppad;
@@ -533,6 +571,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         else if (tid == 8) part[P::C_ACTOR + P::C_NET + H] = sv;                    // critic head bias
     }
     if (warp == 1) umma::tmem_dealloc(tmem, TC_COLS);
+    TC_KSTAMP(5);
     if (!g.tail.enabled) return;
 
     // ================= in-kernel tail: fold partials, [all-reduce over NVLink peer memory], clip, Adam =================
@@ -556,6 +595,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         named_bar_sync(BAR_TAIL, TC_COMPUTE);
     };
     grid_barrier(tl.ctr + 0);                     // every CTA's partial gradient is in global memory
+    TC_KSTAMP(6);
     const int chunk = (PP + nparts - 1) / nparts;
     const int p_lo = blockIdx.x * chunk, p_hi = min(PP, p_lo + chunk);
     const int pl = tid & 63, sl = tid >> 6;        // parameter within a group of 64, slice of the partials (8 slices)
@@ -594,6 +634,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         }
         named_bar_sync(BAR_TAIL, TC_COMPUTE);
     }
+    TC_KSTAMP(7);
     if (multi) {
         // ---- one-shot all-reduce over NVLink: publish, signal every peer, wait for every peer, sum in rank order ----
         __threadfence_system();
@@ -628,7 +669,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         for (int wv = 0; wv < TC_COMPUTE / 32; ++wv) t += dred[wv];
         tl.cta_sumsq[blockIdx.x] = t;
     }
+    TC_KSTAMP(8);
     grid_barrier(tl.ctr + 2);                     // every CTA's squared-norm share is published
+    TC_KSTAMP(9);
     if (warp == 0) {
         double tot = 0.0;
         for (int i = lane; i < nparts; i += 32) tot += __ldcg(tl.cta_sumsq + i);
@@ -657,6 +700,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppo_grad_tc_kernel(GradArgs g) 
         ad.m[p] = m; ad.v[p] = v; ad.params[p] = wgt;
         if (ad.packed != nullptr) packed_store<O, A>(ad.packed, p, wgt);
     }
+    TC_KSTAMP(10);
     if (blockIdx.x == 0 && tid == 0 && tl.loss_terms_out != nullptr) {
         const float inv = 1.0f / (float)g.mb_count;
         const float pg = sbc[4] * inv, vl = 0.5f * sbc[5] * inv, en = sbc[6] * inv;
@@ -680,7 +724,7 @@ static int launch_tc_fused(GradArgs& g, cudaStream_t st) {
     if (grid > MAX_GRAD_CTAS) grid = MAX_GRAD_CTAS;
     if ((uint32_t)grid > ntiles) grid = (int)ntiles;
     void* args[] = {&g};
-    DRL_CUDA(cudaLaunchCooperativeKernel((const void*)ppo_grad_tc_kernel<O, A, OP, RW>, dim3(grid), dim3(TC_THREADS), args, (size_t)smem, st));
+    DRL_CUDA(cudaLaunchCooperativeKernel((const void*)ppo_grad_tc_kernel<O, A, OP, RW>, dim3(grid), dim3(GRAD_TC_BLOCK), args, (size_t)smem, st));
     return DRL_OK;
 }
 
@@ -697,7 +741,7 @@ static int launch_tc(const GradArgs& g, int P, float* grad_out, float* loss_term
     int grid = sm_count();
     if (grid > MAX_GRAD_CTAS) grid = MAX_GRAD_CTAS;
     if ((uint32_t)grid > ntiles) grid = (int)ntiles;
-    ppo_grad_tc_kernel<O, A, OP, RW><<<grid, TC_THREADS, smem, st>>>(g);
+    ppo_grad_tc_kernel<O, A, OP, RW><<<grid, GRAD_TC_BLOCK, smem, st>>>(g);
     DRL_LAUNCH_CHECK("ppo_grad_tc_kernel");
     if (grid_out != nullptr) { *grid_out = grid; return DRL_OK; }
     return launch_grad_reduce(g, grid, P, grad_out, loss_terms_out, st);

@@ -14,6 +14,8 @@ from deep_rl_b200 import _lib as L  # noqa: E402
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 cfg = drl.PPOConfig(num_envs=N, num_steps=128, total_timesteps=N * 128 * 8)
 tr = drl.PPOTrainer(cfg)
+if os.environ.get("DRL_TC_PROBE"):   # the issuer waits for dh1 right after committing it and stamps the completion
+    tr.workspace[-8:] = torch.tensor(list((77).to_bytes(8, "little")), dtype=torch.uint8, device=tr.workspace.device)
 for _ in range(3):
     tr.update()
 torch.cuda.synchronize()
@@ -22,9 +24,16 @@ dbg = ws[-4096:].view(np.int64)
 comp, mma = dbg[:256].reshape(16, 16), dbg[256:].reshape(16, 16)
 t0 = comp[1, 0]
 names_c = ["X start", "fwd ready", "heads done", "pair synced", "dz2 ready", "w1(k-1) ok", "BWD handed", "Z start(Y done)", "bwd ready", "W1 handed"]
-names_m = ["BWD sync", "bwd issued", "FWD sync", "fwd issued", "W1 sync", "w1 issued"]
+names_m = ["BWD sync", "bwd issued", "FWD sync", "fwd issued", "W1 sync", "w1 issued", "(probe) dh1 complete seen by issuer", "C dh1 wait passed"]
 for k in range(1, 6):
     print(f"--- tile {k} (cycles relative to X start of tile 1)")
-    ev = [(int(comp[k, i] - t0), "C " + names_c[i]) for i in range(10)] + [(int(mma[k, i] - t0), "M " + names_m[i]) for i in range(6)]
+    ev = [(int(comp[k, i] - t0), "C " + names_c[i]) for i in range(10)] + [(int(mma[k, i] - t0), "M " + names_m[i]) for i in range(8) if mma[k, i] != 0]
     for t, n in sorted(ev):
         print(f"{t:8d}  {n}")
+
+ks = [int(mma[n >> 3, 8 + (n & 7)]) for n in range(11)]
+kn = ["kernel entry", "first record requested", "weights landed", "main loop start", "main loop end", "partials stored",
+      "grid barrier 0 passed", "fold done", "norm share published", "grid barrier 2 passed", "Adam done"]
+print("--- whole kernel, CTA 0 thread 0 (cycles from kernel entry)")
+for n in range(11):
+    print(f"{ks[n] - ks[0]:8d}  {kn[n]}")
