@@ -47,7 +47,7 @@ struct TcSmem {
     static constexpr int OFF_OBS = OFF_DZ1 + 32768;    // three NS16 buffers [obs_hi|1|obs_lo] (tile % 3)
     static constexpr int OFF_DOUT = OFF_OBS + 12288;   // one NS16 buffer
     static constexpr int OFF_SCAL = OFF_DOUT + 4096;   // three buffers of per-row scalars {logp_old, adv, val_old, act} (16 B each)
-    static constexpr int OFF_BAR = OFF_SCAL + 3 * 2048;   // 12 mbarriers + TMEM slot
+    static constexpr int OFF_BAR = OFF_SCAL + 3 * 2048;   // 13 mbarriers + TMEM slot
     static constexpr int OFF_XCH = OFF_BAR + 128;      // head partial sums [net][half][A][128 rows] fp32
     static constexpr int OFF_RED = OFF_XCH + 2 * 2 * 4 * 128 * 4;
     static constexpr int TOTAL = OFF_RED + 16 * 12 * 4 + 1024;   // + alignment slack
@@ -55,7 +55,7 @@ struct TcSmem {
 };
 
 // diagnostics: cycle stamps of CTA 0 (slot = tile * 16 + event), enabled with DRL_TC_DEBUG=1
-#define TC_STAMP(ev) do { if (g.dbg != nullptr && blockIdx.x == 0 && lane == 0 && k < 12) g.dbg[(warp == 0 ? 0 : 256) + k * 16 + (ev)] = clock64(); } while (0)
+#define TC_STAMP(ev) do { if (g.dbg != nullptr && blockIdx.x == 0 && lane == 0 && k < 12 && (warp == 0 || warp == TC_COMPUTE / 32)) g.dbg[(warp == 0 ? 0 : 256) + k * 16 + (ev)] = clock64(); } while (0)
 
 // whole-kernel stamps of CTA 0 (thread 0): slots 8..15 of the issuer rows of the debug block
 #define TC_KSTAMP(n) do { if (g.dbg != nullptr && blockIdx.x == 0 && tid == 0) g.dbg[256 + ((n) >> 3) * 16 + 8 + ((n) & 7)] = clock64(); } while (0)
@@ -94,10 +94,10 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     unsigned char* tOBS = sm + S::OFF_OBS;
     unsigned char* tDOUT = sm + S::OFF_DOUT;
     uint4* sSCAL = reinterpret_cast<uint4*>(sm + S::OFF_SCAL);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd, 2 dh1, 3 w1, 4 layer 1, 5 dW2/db2/dW4
-    uint64_t* ring_full = bars + 6;                                  // loader -> consumers, one per ring slot (32 arrivals)
-    uint64_t* ring_empty = bars + 6 + RING;                          // tcgen05.commit after the last GEMM reading the slot
-    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * RING);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd, 2 dh1, 3 w1, 4 layer 1, 5 dW4, 6 dW2/db2
+    uint64_t* ring_full = bars + 7;                                  // loader -> consumers, one per ring slot (32 arrivals)
+    uint64_t* ring_empty = bars + 7 + RING;                          // tcgen05.commit after the last GEMM reading the slot
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * RING);
     float* xch = reinterpret_cast<float*>(sm + S::OFF_XCH);
     float* red = reinterpret_cast<float*>(sm + S::OFF_RED);
 
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     TC_KSTAMP(0);
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 7; ++i) mbar_init(bars + i, 1);
 #pragma unroll
         for (int i = 0; i < RING; ++i) { mbar_init(ring_full + i, 32); mbar_init(ring_empty + i, 1); }
         mbar_fence_init();
@@ -244,7 +244,6 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             umma::fence_after_sync();
             TC_STAMP(0);
             if (umma::elect_one()) {
-                const uint32_t h1b = aH1 + par * 32768;
 #pragma unroll
                 for (int n2 = 0; n2 < 2; ++n2)
 #pragma unroll
@@ -252,22 +251,13 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
                         umma::mma(tmem + C_DH + n2 * 64, umma::make_desc(aDZ + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
                                   umma::make_desc(aW2 + n2 * 8192 + kb * 2048, 8192, 1024, umma::LAYOUT_SW128), ID_DH1, kb > 0);
                 umma::commit(bars + 2);          // dh1 is all that Z(k) waits for
-#pragma unroll
-                for (int kb = 0; kb < 8; ++kb)
-                    umma::mma(tmem + C_W2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
-                              umma::make_desc(h1b + kb * 2048, 16384, 1024, umma::LAYOUT_SW128), ID_W2, acc | (kb > 0));
-#pragma unroll
-                for (int kb = 0; kb < 8; ++kb)
-                    umma::mma(tmem + C_B2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
-                              umma::make_desc(obsb + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
-#pragma unroll
-                for (int kb = 0; kb < 8; ++kb)
-                    umma::mma(tmem + C_W4, umma::make_desc(aH2 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
-                              umma::make_desc(aDOUT + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
-                umma::commit(bars + 5);          // weight-gradient GEMMs: only gate the reuse of their operand tiles
+                if (g.dbg != nullptr && blockIdx.x == 0 && k < 12) g.dbg[256 + k * 16 + 6] = clock64();
             }
             __syncwarp();
             TC_STAMP(1);
+            // fwd(k+1) is what X(k+1) waits for: it goes ahead of the weight-gradient GEMMs of tile k, which nobody needs
+            // until late in X(k+1).  (All GEMM groups compete with the compute warps for shared-memory bandwidth -- a group
+            // takes ~600 cycles alone and up to twice that with other groups queued behind it.)
             if (k + 1 < nmy) {
                 named_bar_sync(BAR_FWD, TC_THREADS);
                 umma::fence_after_sync();
@@ -276,6 +266,24 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
                 __syncwarp();
                 TC_STAMP(3);
             }
+            if (umma::elect_one()) {
+                const uint32_t h1b = aH1 + par * 32768;
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb)
+                    umma::mma(tmem + C_W4, umma::make_desc(aH2 + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                              umma::make_desc(aDOUT + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
+                umma::commit(bars + 5);          // h2 and dout tiles may be overwritten (early in X(k+1))
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb)
+                    umma::mma(tmem + C_W2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                              umma::make_desc(h1b + kb * 2048, 16384, 1024, umma::LAYOUT_SW128), ID_W2, acc | (kb > 0));
+#pragma unroll
+                for (int kb = 0; kb < 8; ++kb)
+                    umma::mma(tmem + C_B2, umma::make_desc(aDZ + kb * 2048, 16384, 1024, umma::LAYOUT_SW128),
+                              umma::make_desc(obsb + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0));
+                umma::commit(bars + 6);          // dz2 and h1(k) tiles may be overwritten (end of X(k+1), Y(k+1))
+            }
+            __syncwarp();
             named_bar_sync(BAR_W1, TC_THREADS);
             umma::fence_after_sync();
             TC_STAMP(4);
@@ -334,7 +342,6 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         // ================= X(k): heads, loss, output gradients, dz2 =================
         TC_STAMP(0);
         mbar_wait(bars + 1, par);
-        if (k > 0) mbar_wait(bars + 5, (k - 1) & 1u);   // dW2/db2/dW4(k-1) have finished reading the h2, dz2, dout, h1 tiles
         umma::fence_after_sync();
         TC_STAMP(1);
         {
@@ -353,6 +360,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
                 h[4 * k4 + 2] = tanh_mufu(h[4 * k4 + 2] + bb.z);
                 h[4 * k4 + 3] = tanh_mufu(h[4 * k4 + 3] + bb.w);
             }
+            if (k > 0) mbar_wait(bars + 5, (k - 1) & 1u);   // dW4(k-1) has finished reading the h2 and dout tiles
             store_half_row_sw128(tH2 + net * 16384, r, half * 4, h);
 
             // head partial sums over this thread's 32 units, exchanged with the thread owning the other 32
@@ -473,6 +481,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             }
             TC_STAMP(4);
             TC_STAMP(5);
+            if (k > 0) mbar_wait(bars + 6, (k - 1) & 1u);   // dW2/db2(k-1) have finished reading the dz2 and h1(k-1) tiles
             store_half_row_sw128(tDZ + net * 16384, r, half * 4, h);
         }
         umma::fence_proxy_async();
@@ -492,7 +501,9 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             uint4 hq[4];                                   // this thread's h1 values (bf16): loaded before the wait
 #pragma unroll
             for (int c = 0; c < 4; ++c) hq[c] = *reinterpret_cast<const uint4*>(h1row + umma::sw128_off(r, half * 4 + c));
+            TC_STAMP(10);
             mbar_wait(bars + 2, par);
+            TC_STAMP(11);
             if (k > 0) mbar_wait(bars + 3, (k - 1) & 1u);   // w1(k-1) has finished reading tDZ1
             umma::fence_after_sync();
             TC_STAMP(8);
@@ -521,6 +532,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     }
     mbar_wait(bars + 3, (nmy - 1) & 1u);
     mbar_wait(bars + 5, (nmy - 1) & 1u);
+    mbar_wait(bars + 6, (nmy - 1) & 1u);
     umma::fence_after_sync();
     TC_KSTAMP(4);
 

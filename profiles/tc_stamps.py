@@ -23,11 +23,11 @@ ws = tr.workspace.cpu().numpy()
 dbg = ws[-4096:].view(np.int64)
 comp, mma = dbg[:256].reshape(16, 16), dbg[256:].reshape(16, 16)
 t0 = comp[1, 0]
-names_c = ["X start", "fwd ready", "heads done", "pair synced", "dz2 ready", "w1(k-1) ok", "BWD handed", "Z start(Y done)", "bwd ready", "W1 handed"]
-names_m = ["BWD sync", "bwd issued", "FWD sync", "fwd issued", "W1 sync", "w1 issued", "(probe) dh1 complete seen by issuer", "C dh1 wait passed"]
+names_c = ["X start", "fwd ready", "heads done", "pair synced", "dz2 ready", "w1(k-1) ok", "BWD handed", "Z start(Y done)", "bwd ready", "W1 handed", "Z: before dh1 wait", "Z: dh1 wait passed"]
+names_m = ["BWD sync", "bwd issued", "FWD sync", "fwd issued", "W1 sync", "w1 issued", "dh1 issued + committed"]
 for k in range(1, 6):
     print(f"--- tile {k} (cycles relative to X start of tile 1)")
-    ev = [(int(comp[k, i] - t0), "C " + names_c[i]) for i in range(10)] + [(int(mma[k, i] - t0), "M " + names_m[i]) for i in range(8) if mma[k, i] != 0]
+    ev = [(int(comp[k, i] - t0), "C " + names_c[i]) for i in range(12)] + [(int(mma[k, i] - t0), "M " + names_m[i]) for i in range(7) if mma[k, i] != 0]
     for t, n in sorted(ev):
         print(f"{t:8d}  {n}")
 

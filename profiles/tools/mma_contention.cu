@@ -6,7 +6,7 @@
 #include "drl_umma.cuh"
 
 using namespace drl;
-constexpr int NMODE = 9, REP = 4;
+constexpr int NMODE = 13, REP = 4;
 
 __global__ void __launch_bounds__(544) contention_kernel(int mode, long long* out, float* sink) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -15,7 +15,13 @@ __global__ void __launch_bounds__(544) contention_kernel(int mode, long long* ou
     uint32_t* slot = reinterpret_cast<uint32_t*>(sm + 163840 + 32);
     volatile int* stop = reinterpret_cast<volatile int*>(sm + 163840 + 64);
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < 163840 / 4; i += 544) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u + i % 7;
+    for (int i = tid; i < 163840 / 4; i += 544) {
+        uint32_t v = 0x3c003c00u + i % 7;
+        if (mode == 9) v = 0x322b322bu + (i % 5) * 0x00010001u;                       // ~1e-8: the magnitude of real dz2 values
+        if (mode == 10) { v = (uint32_t)i * 2654435761u; v ^= v >> 13; v &= 0xBF7FBF7Fu; }   // random finite bf16 pairs
+        if (mode == 11) v = 0x00010001u * (1 + i % 3);                                // bf16 denormals
+        reinterpret_cast<uint32_t*>(sm)[i] = v;
+    }
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); *stop = 0; }
     if (warp == 1) umma::tmem_alloc(slot, 512);
     umma::fence_proxy_async();
@@ -32,6 +38,7 @@ __global__ void __launch_bounds__(544) contention_kernel(int mode, long long* ou
             for (int gk = 0; gk < 2; ++gk)
                 for (int rep = 0; rep < REP; ++rep) {
                     const long long t0 = clock64();
+                    *reinterpret_cast<volatile long long*>(sm + 163840 + 72) = t0;
                     if (gk == 0) {
                         for (int n2 = 0; n2 < 2; ++n2)
                             for (int kb = 0; kb < 4; ++kb)
@@ -59,6 +66,17 @@ __global__ void __launch_bounds__(544) contention_kernel(int mode, long long* ou
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         float acc = (float)tid;
         unsigned char* scratch = sm + 98304 + (size_t)tid * 16;     // 8 KB region away from the operand tiles
+        if (mode == 12) {      // all 512 compute threads wait on the commit barrier, like Z(k) of the update kernel
+            volatile long long* t0s = reinterpret_cast<volatile long long*>(sm + 163840 + 72);
+            uint32_t ph = 0;
+            for (int i = 0; i < 2 * REP; ++i) {
+                mbar_wait(bar, ph);
+                ph ^= 1u;
+                const long long t = clock64();
+                if (tid == 0) out[16 + i] = t - *t0s;
+                if (tid == 511) out[32 + i] = t - *t0s;
+            }
+        }
         while (*stop == 0) {
             if (mode == 1) {
                 float v[32];
@@ -96,14 +114,14 @@ __global__ void __launch_bounds__(544) contention_kernel(int mode, long long* ou
 
 int main() {
     long long* d; float* sink;
-    cudaMalloc(&d, 2 * REP * 2 * sizeof(long long));
+    cudaMalloc(&d, 64 * sizeof(long long));
     cudaMalloc(&sink, 544 * 4);
     const int smem = 163840 + 128 + 1024;
     cudaFuncSetAttribute(contention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    const char* names[NMODE] = {"idle (nanosleep)", "tcgen05.ld loop", "MUFU tanh loop", "st.shared.v4 loop", "ld.shared.v4 loop", "FFMA loop", "MUFU burst, all warps", "MUFU burst, SMSP 1-3", "MUFU burst, SMSP 0"};
+    const char* names[NMODE] = {"idle (nanosleep)", "tcgen05.ld loop", "MUFU tanh loop", "st.shared.v4 loop", "ld.shared.v4 loop", "FFMA loop", "MUFU burst, all warps", "MUFU burst, SMSP 1-3", "MUFU burst, SMSP 0", "idle, operands ~1e-8", "idle, random operands", "idle, denormal operands", "512 threads wait on the barrier"};
     for (int mode = 0; mode < NMODE; ++mode) {
         contention_kernel<<<1, 544, smem>>>(mode, d, sink);
-        long long h[2 * REP * 2];
+        long long h[64];
         cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
         printf("%-20s fwd issue/complete:", names[mode]);
@@ -111,6 +129,11 @@ int main() {
         printf("   dh1:");
         for (int rep = 0; rep < REP; ++rep) printf(" %lld/%lld", h[(REP + rep) * 2], h[(REP + rep) * 2 + 1]);
         printf("\n");
+        if (mode == 12) {
+            printf("   seen by waiting compute thread 0 / 511:");
+            for (int i = 0; i < 2 * REP; ++i) printf(" %lld/%lld", h[16 + i], h[32 + i]);
+            printf("\n");
+        }
     }
     return 0;
 }
