@@ -537,31 +537,35 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     TC_KSTAMP(4);
 
     // ================= epilogue: this CTA's partial gradient, canonical layout =================
+    // Staged in shared memory (the tiles are dead), then copied out with coalesced stores.  A thread owns 32 consecutive
+    // W2 columns of one row, so the W2 blocks are staged with the column XOR-swizzled by the row: conflict-free both ways.
+    float* stage = reinterpret_cast<float*>(sm + S::OFF_H1);
     float* part = g.grad_part + (size_t)blockIdx.x * g.ppad;
     const int no = r >> 6, o = r & 63;                 // TMEM lane r = hidden unit o of net `no`
+    constexpr int W2_OFF = H * O + H;                  // offset of W2 inside a net's canonical block
     if (warp < 4) {
         const int base = no * P::C_ACTOR;
         float v16[16];
         umma::ld16(trow + C_B2, v16);
-        part[base + H * O + H + H * H + o] = v16[O];   // db2
+        stage[base + H * O + H + H * H + o] = v16[O];   // db2
         umma::ld16(trow + C_W1, v16);
 #pragma unroll
-        for (int i = 0; i < O; ++i) part[base + o * O + i] = v16[i] + v16[8 + i];   // dW1 = dz1^T . (obs_hi + obs_lo)
-        part[base + H * O + o] = v16[O];                               // db1
+        for (int i = 0; i < O; ++i) stage[base + o * O + i] = v16[i] + v16[8 + i];   // dW1 = dz1^T . (obs_hi + obs_lo)
+        stage[base + H * O + o] = v16[O];                               // db1
         umma::ld16(trow + C_W4, v16);
         if (no == 0) {
 #pragma unroll
-            for (int a = 0; a < A; ++a) part[P::C_NET + a * H + o] = v16[a];   // actor head
+            for (int a = 0; a < A; ++a) stage[P::C_NET + a * H + o] = v16[a];   // actor head
         } else {
-            part[P::C_ACTOR + P::C_NET + o] = v16[8];                           // critic head
+            stage[P::C_ACTOR + P::C_NET + o] = v16[8];                           // critic head
         }
     }
     if (no == net) {   // dW2: the diagonal 64x64 blocks of the 128x128 accumulator (warp-uniform branch)
         float v[HU];
         umma::ld32(trow + C_W2 + net * 64 + u0, v);
-        float* dst = part + net * P::C_ACTOR + H * O + H + o * H + u0;
+        float* dst = stage + net * P::C_ACTOR + W2_OFF + o * H;
 #pragma unroll
-        for (int i = 0; i < HU; ++i) dst[i] = v[i];
+        for (int i = 0; i < HU; ++i) dst[(u0 + i) ^ (o & 31)] = v[i];
     }
     // loss partial sums and head-bias gradients: fold the 512 compute threads
     {
@@ -579,8 +583,16 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
 #pragma unroll
         for (int w = 0; w < TC_COMPUTE / 32; ++w) sv += red[w * 12 + tid];
         if (tid < 5) g.loss_part[blockIdx.x * LOSS_TERMS + tid] = sv;
-        else if (tid - 5 < A) part[P::C_NET + A * H + (tid - 5)] = sv;              // actor head bias
-        else if (tid == 8) part[P::C_ACTOR + P::C_NET + H] = sv;                    // critic head bias
+        else if (tid - 5 < A) stage[P::C_NET + A * H + (tid - 5)] = sv;              // actor head bias
+        else if (tid == 8) stage[P::C_ACTOR + P::C_NET + H] = sv;                    // critic head bias
+    }
+    named_bar_sync(13, TC_COMPUTE);       // only the compute warps are left
+    for (int i = tid; i < P::C_ALL; i += TC_COMPUTE) {
+        const int nb = i >= P::C_ACTOR ? 1 : 0;
+        const int w = i - nb * P::C_ACTOR - W2_OFF;    // index inside this net's W2 block, if 0 <= w < H*H
+        int src = i;
+        if (w >= 0 && w < H * H) src = i - (w & 63) + ((w & 63) ^ ((w >> 6) & 31));
+        part[i] = stage[src];
     }
     if (warp == 1) umma::tmem_dealloc(tmem, TC_COLS);
     TC_KSTAMP(5);

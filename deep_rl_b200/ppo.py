@@ -18,6 +18,7 @@ Run as a script:  python -m deep_rl_b200.ppo [--num-envs N] [--total-timesteps K
 from __future__ import annotations
 
 import argparse
+import contextlib
 import ctypes as C
 import math
 from dataclasses import dataclass
@@ -51,6 +52,8 @@ class PPOConfig:
     anneal_lr: bool = True
     rollout_precision: str = "auto"  # "bf16": tcgen05 rollout (32-128 envs per CTA); "fp32": CUDA-core rollout; "auto": bf16 when
                                      # the update is bf16 and there are at least 2048 envs
+    overlap_streams: bool = True     # permutations (during the rollout) and advantage statistics of later epochs (during the
+                                     # minibatch steps of earlier ones) run on a second CUDA stream
     grad_allreduce: str = "peer"     # multi-GPU gradient exchange: "peer" = one-shot all-reduce over NVLink peer memory inside
                                      # the gradient kernel (bf16 update only), "nccl" = NCCL all-reduce between kernels
     update_precision: str = "bf16"   # "bf16": tcgen05 tensor-core update (bf16 operands, fp32 accumulate); "fp32": CUDA-core update
@@ -120,9 +123,14 @@ class PPOTrainer:
         B = cfg.batch_size
         self.RW = self.L.drl_record_width(C.byref(self.net))
         self.records = torch.zeros((B, self.RW), dtype=f32, device=dev)
-        self.idx = torch.zeros(B, dtype=torch.int32, device=dev)
         self.n_mb = (B + cfg.minibatch_size - 1) // cfg.minibatch_size
-        self.adv_stats = torch.zeros((self.n_mb, 2), dtype=f32, device=dev)
+        # one index array and one statistics block per epoch: they are produced ahead of the epoch that consumes them
+        self.idx = torch.zeros((cfg.update_epochs, B), dtype=torch.int32, device=dev)
+        self.adv_stats = torch.zeros((cfg.update_epochs, self.n_mb, 2), dtype=f32, device=dev)
+        self.side = torch.cuda.Stream(device=dev) if cfg.overlap_streams else None
+        self._ev_gae = torch.cuda.Event()
+        self._ev_stats = [torch.cuda.Event() for _ in range(cfg.update_epochs)]
+        self._perms_scheduled = False
         P = agent.flat_params.numel()
         self.grad = torch.zeros(P, dtype=f32, device=dev)
         self.exp_avg = torch.zeros(P, dtype=f32, device=dev)
@@ -191,23 +199,65 @@ class PPOTrainer:
                                       self.records.data_ptr(), _lib.stream_ptr()))
         self.kernel_launches += 1
 
-    def optimize(self, lr: float) -> None:
-        """ppo.py:154-192."""
-        cfg, st = self.cfg, _lib.stream_ptr()
+    def _side(self):
+        return torch.cuda.stream(self.side) if self.side is not None else contextlib.nullcontext()
+
+    def schedule_permutations(self) -> None:
+        """ppo.py:155 for every epoch of the coming update.  The keyed permutation depends on counters only, so with
+        `overlap_streams` it runs on the side stream while the rollout kernel runs on the main one."""
+        cfg = self.cfg
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())     # the previous update has finished reading idx / adv_stats
+        with self._side():
+            st = _lib.stream_ptr()
+            for epoch in range(cfg.update_epochs):
+                epoch_ctr = self.update_idx * cfg.update_epochs + epoch
+                with _Phase(self, "permutation"):
+                    _lib.check(self.L.drl_permutation(self.idx[epoch].data_ptr(), cfg.batch_size, cfg.seed, epoch_ctr, self.rank, st))
+        self.kernel_launches += cfg.update_epochs
+        self._perms_scheduled = True
+
+    def schedule_adv_stats(self) -> None:
+        """ppo.py:169 statistics of every (epoch, minibatch): needs the advantages, i.e. runs after GAE; epoch e + 1's pass
+        overlaps epoch e's minibatch steps on the side stream."""
+        cfg = self.cfg
         B, M = cfg.batch_size, cfg.minibatch_size
         net = C.byref(self.net)
+        if self.side is not None:
+            self._ev_gae.record()
+            self.side.wait_event(self._ev_gae)
+        with self._side():
+            st = _lib.stream_ptr()
+            for epoch in range(cfg.update_epochs):
+                epoch_ctr = self.update_idx * cfg.update_epochs + epoch
+                with _Phase(self, "adv_stats"):
+                    if self.n_mb <= 8:   # no gather: natural-order pass over the advantage plane + inverse permutation
+                        _lib.check(self.L.drl_adv_stats_perm(net, self.advantages.data_ptr(), B, M, cfg.seed, epoch_ctr, self.rank,
+                                                             self.adv_stats[epoch].data_ptr(), self.workspace.data_ptr(),
+                                                             self.ws_bytes, st))
+                    else:
+                        _lib.check(self.L.drl_adv_stats(net, self.records.data_ptr(), self.idx[epoch].data_ptr(), B, M,
+                                                        self.adv_stats[epoch].data_ptr(), self.workspace.data_ptr(),
+                                                        self.ws_bytes, st))
+                if self.side is not None:
+                    self._ev_stats[epoch].record()
+        self.kernel_launches += cfg.update_epochs
+
+    def optimize(self, lr: float) -> None:
+        """ppo.py:154-192."""
+        cfg = self.cfg
+        B, M = cfg.batch_size, cfg.minibatch_size
+        net = C.byref(self.net)
+        if not self._perms_scheduled:
+            self.schedule_permutations()
+        self._perms_scheduled = False
+        self.schedule_adv_stats()
+        st = _lib.stream_ptr()
         for epoch in range(cfg.update_epochs):
-            epoch_ctr = self.update_idx * cfg.update_epochs + epoch
-            with _Phase(self, "permutation"):
-                _lib.check(self.L.drl_permutation(self.idx.data_ptr(), B, cfg.seed, epoch_ctr, self.rank, st))
-            with _Phase(self, "adv_stats"):
-                if self.n_mb <= 8:   # no gather: natural-order pass over the advantage plane + inverse permutation
-                    _lib.check(self.L.drl_adv_stats_perm(net, self.advantages.data_ptr(), B, M, cfg.seed, epoch_ctr, self.rank,
-                                                         self.adv_stats.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, st))
-                else:
-                    _lib.check(self.L.drl_adv_stats(net, self.records.data_ptr(), self.idx.data_ptr(), B, M,
-                                                    self.adv_stats.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, st))
-            self.kernel_launches += 2
+            if self.side is not None:
+                torch.cuda.current_stream().wait_event(self._ev_stats[epoch])
+            idx_ptr = self.idx[epoch].data_ptr()
+            stats_ptr = self.adv_stats[epoch].data_ptr()
             for k in range(self.n_mb):
                 start = k * M
                 count = min(M, B - start)
@@ -216,8 +266,8 @@ class PPOTrainer:
                     self.adam_step += 1
                     with _Phase(self, "minibatch_grad"):    # gradient + fold + NVLink all-reduce + clip + Adam: one launch
                         _lib.check(self.L.drl_ppo_minibatch_update_dist(
-                            net, self.agent.packed.data_ptr(), self.records.data_ptr(), self.idx.data_ptr(), start, count,
-                            self.adv_stats.data_ptr() + 8 * k, C.byref(self.coef), self.agent.flat_params.data_ptr(),
+                            net, self.agent.packed.data_ptr(), self.records.data_ptr(), idx_ptr, start, count,
+                            stats_ptr + 8 * k, C.byref(self.coef), self.agent.flat_params.data_ptr(),
                             self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.adam_step, lr,
                             0.9, 0.999, 1e-5, cfg.max_grad_norm, self.loss_terms.data_ptr() + 32 * row,
                             self.grad_norm.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, self.grad_flags,
@@ -228,8 +278,8 @@ class PPOTrainer:
                     self.adam_step += 1
                     with _Phase(self, "minibatch_grad"):    # gradient kernel + fused fold/clip/Adam kernel
                         _lib.check(self.L.drl_ppo_minibatch_update(
-                            net, self.agent.packed.data_ptr(), self.records.data_ptr(), self.idx.data_ptr(), start, count,
-                            self.adv_stats.data_ptr() + 8 * k, C.byref(self.coef), self.agent.flat_params.data_ptr(),
+                            net, self.agent.packed.data_ptr(), self.records.data_ptr(), idx_ptr, start, count,
+                            stats_ptr + 8 * k, C.byref(self.coef), self.agent.flat_params.data_ptr(),
                             self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.adam_step, lr,
                             0.9, 0.999, 1e-5, cfg.max_grad_norm, self.loss_terms.data_ptr() + 32 * row,
                             self.grad_norm.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, self.grad_flags, st))
@@ -237,8 +287,8 @@ class PPOTrainer:
                     continue
                 with _Phase(self, "minibatch_grad"):
                     _lib.check(self.L.drl_ppo_minibatch_grad(
-                        net, self.agent.packed.data_ptr(), self.records.data_ptr(), self.idx.data_ptr(), start, count,
-                        self.adv_stats.data_ptr() + 8 * k, C.byref(self.coef), self.grad.data_ptr(),
+                        net, self.agent.packed.data_ptr(), self.records.data_ptr(), idx_ptr, start, count,
+                        stats_ptr + 8 * k, C.byref(self.coef), self.grad.data_ptr(),
                         self.loss_terms.data_ptr() + 32 * row, self.workspace.data_ptr(), self.ws_bytes, self.grad_flags, st))
                 if self.world > 1:
                     with _Phase(self, "allreduce"):
@@ -255,6 +305,7 @@ class PPOTrainer:
         """One full update (rollout + GAE + epochs), asynchronous: no host synchronisation."""
         nu = num_updates if num_updates is not None else max(1, self.cfg.num_updates(self.world))
         lr = self.learning_rate(self.update_idx, nu)
+        self.schedule_permutations()
         self.rollout()
         self.compute_gae()
         self.optimize(lr)
