@@ -632,15 +632,29 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         const int p = p0 + pl;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (p < p_hi) {
-            int c = sl;
-            for (; c + 24 < nparts; c += 32) {
-                const float v0 = __ldcg(g.grad_part + (size_t)c * g.ppad + p);
-                const float v1 = __ldcg(g.grad_part + (size_t)(c + 8) * g.ppad + p);
-                const float v2 = __ldcg(g.grad_part + (size_t)(c + 16) * g.ppad + p);
-                const float v3 = __ldcg(g.grad_part + (size_t)(c + 24) * g.ppad + p);
-                a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+            // all (up to 20) loads of this thread in flight at once: one L2 round trip instead of seven.  The summation
+            // keeps the association of grad_reduce_kernel: four interleaved accumulators over groups of 32 partials while a
+            // whole group fits, then the remaining partials one by one into the first accumulator.
+            static_assert(MAX_GRAD_CTAS <= 160, "fold is unrolled for at most 160 partials");
+            float pv[20];
+#pragma unroll
+            for (int j = 0; j < 20; ++j) {
+                const int c = sl + 8 * j;
+                pv[j] = c < nparts ? __ldcg(g.grad_part + (size_t)c * g.ppad + p) : 0.0f;
             }
-            for (; c < nparts; c += 8) a0 += __ldcg(g.grad_part + (size_t)c * g.ppad + p);
+            bool rest = false;
+#pragma unroll
+            for (int gq = 0; gq < 5; ++gq) {
+                const int c = sl + 32 * gq;
+                if (!rest && c + 24 < nparts) {
+                    a0 += pv[4 * gq]; a1 += pv[4 * gq + 1]; a2 += pv[4 * gq + 2]; a3 += pv[4 * gq + 3];
+                } else {
+                    rest = true;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (c + 8 * q < nparts) a0 += pv[4 * gq + q];
+                }
+            }
         }
         tred[sl * 64 + pl] = (a0 + a1) + (a2 + a3);
         named_bar_sync(BAR_TAIL, TC_COMPUTE);
@@ -694,6 +708,10 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         tl.cta_sumsq[blockIdx.x] = t;
     }
     TC_KSTAMP(8);
+    // optimizer state of this thread's first parameter: fetched before the barrier, it does not depend on the norm
+    const int p_first = p_lo + tid;
+    float pre_m = 0.f, pre_v = 0.f, pre_w = 0.f;
+    if (p_first < p_hi) { pre_m = ad.m[p_first]; pre_v = ad.v[p_first]; pre_w = ad.params[p_first]; }
     grid_barrier(tl.ctr + 2);                     // every CTA's squared-norm share is published
     TC_KSTAMP(9);
     if (warp == 0) {
@@ -716,7 +734,9 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     const float coef = sbc[0];
     for (int p = p_lo + tid; p < p_hi; p += TC_COMPUTE) {
         const float gsc = (__ldcg(tl.grad_out + p) * ad.grad_scale) * coef;
-        float m = ad.m[p], v = ad.v[p], wgt = ad.params[p];
+        float m, v, wgt;
+        if (p == p_first) { m = pre_m; v = pre_v; wgt = pre_w; }
+        else { m = ad.m[p]; v = ad.v[p]; wgt = ad.params[p]; }
         m = m + ad.om_beta1 * (gsc - m);
         v = v * ad.beta2 + (ad.om_beta2 * gsc) * gsc;
         const float denom = sqrtf(v) / ad.bc2_sqrt + ad.eps;
