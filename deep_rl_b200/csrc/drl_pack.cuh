@@ -69,7 +69,7 @@ constexpr int STAT_PARTS = 512;      // max partial-sum CTAs per minibatch in dr
 constexpr int LOSS_TERMS = 8;
 
 struct WorkspaceLayout {
-    size_t counters, stat_partials, loss_partials, grad_partials, debug, total;
+    size_t counters, stat_partials, cta_sumsq, loss_partials, grad_partials, debug, total;
     int ppad;
 };
 inline WorkspaceLayout workspace_layout(int64_t P) {
@@ -77,7 +77,10 @@ inline WorkspaceLayout workspace_layout(int64_t P) {
     w.ppad = (int)((P + 3) / 4 * 4);
     w.counters = 0;
     w.stat_partials = 64;
-    w.loss_partials = w.stat_partials + sizeof(double) * MAX_MINIBATCHES * STAT_PARTS * 2;
+    // squared-norm shares of the fused clip+Adam steps: their own region, the statistics of a later epoch may run on
+    // another stream while a minibatch step is in flight
+    w.cta_sumsq = w.stat_partials + sizeof(double) * MAX_MINIBATCHES * STAT_PARTS * 2;
+    w.loss_partials = w.cta_sumsq + sizeof(double) * 1024;
     w.grad_partials = w.loss_partials + sizeof(float) * MAX_GRAD_CTAS * LOSS_TERMS;
     w.debug = w.grad_partials + sizeof(float) * (size_t)MAX_GRAD_CTAS * w.ppad;   // 4 KB of cycle stamps (DRL_TC_DEBUG=1)
     w.total = w.debug + 4096;

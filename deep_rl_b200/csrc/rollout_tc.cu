@@ -3,14 +3,18 @@
 // hidden layers run on tcgen05 (bf16 operands, fp32 TMEM accumulators) with the same numerics as the tensor-core
 // update (update_tc.cu), so log-probs recorded here and re-evaluated there agree to bf16 rounding.
 //
-// One CTA = 128 environments (the 128 TMEM lanes) for all T steps; 16 compute warps + 1 MMA-issuer warp.
-// Compute thread (warp w, lane l): env row r = 32*(w&3)+l, net = w>>3, hidden units [32*((w>>2)&1), +32).
-// Warps 0-3 (actor, first half) additionally own the env state (float64 registers).  Per step:
+// One CTA = 128 / REP environments for all T steps; 16 compute warps + 1 MMA-issuer warp.  The GEMM tile always has the
+// 128 rows of the TMEM lanes; with REP > 1 every environment occupies REP rows (one per lane quadrant group), so that
+// REP times as many threads share its per-step work -- with few environments per GPU the per-step latency, not the
+// throughput, sets the pace, and a warp can only read the TMEM lanes of its own quadrant.
+// Compute thread (warp w, lane l): quadrant q = w&3 (TMEM lanes [32q, 32q+32)), half = (w>>2)&1, net = w>>3;
+//   env row  e = 32*(q mod 4/REP) + l,  replica = q div (4/REP),  hidden units [32*half + replica*32/REP, +32/REP).
+// The threads with half = net = replica = 0 additionally own the env state (float64 registers).  Per step:
 //   S0  owners: observation from state -> obs[t] in HBM and the fp32 obs tile in shared memory
-//   --  row-window barrier (the 4 warps that share 32 rows)
-//   S1  all: layer 1 on CUDA cores for 32 units -> bf16 SW128 tile; hand the forward GEMM to the issuer warp
+//   --  group barrier (the 4*REP warps that share 32 environments)
+//   S1  all: layer 1 on CUDA cores for 32/REP units -> bf16 SW128 tile (all REP rows of the env); hand the forward GEMM
 //   S2  all: wait, tcgen05.ld z2, tanh, partial head dot products -> exchange buffer
-//   --  row-window barrier
+//   --  group barrier
 //   S3  owners: logits / value, value store, Philox inverse-CDF sample, log-prob, fp64 env step with auto-reset
 //       and episode statistics, reward / done stores
 #include "drl_env.cuh"
@@ -31,21 +35,24 @@ struct RoTcSmem {
     static constexpr int OFF_W = 0;
     static constexpr int OFF_H1 = (OFF_W + W_BYTES + 1023) / 1024 * 1024;   // (actor, critic) x 16 KB
     static constexpr int OFF_OBS = OFF_H1 + 32768;                           // fp32 [128][OW]
-    static constexpr int OFF_XCH = OFF_OBS + TC_TILE * P::OW * 4;            // fp32 [8][128] head partial sums
-    static constexpr int OFF_BAR = OFF_XCH + 8 * TC_TILE * 4;
+    static constexpr int OFF_XCH = OFF_OBS + TC_TILE * P::OW * 4;            // fp32 [32 slots][128] head partial sums
+    static constexpr int OFF_BAR = OFF_XCH + 32 * TC_TILE * 4;
     static constexpr int TOTAL = OFF_BAR + 64 + 1024;
 };
 
-template <int KIND>
+template <int KIND, int REP>
 __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env, const float* __restrict__ packed, int T,
-                                                                   uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log,
-                                                                   int rows) {
+                                                                   uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log) {
     using SP = EnvSpec<KIND>;
     constexpr int O = SP::O, A = SP::A, OP = SP::OP;
     using P = Packed<O, A>;
     using S = RoTcSmem<O, A>;
     constexpr int OW = P::OW;
+    constexpr int ROWS = TC_TILE / REP;       // environments per CTA
+    constexpr int QG = 4 / REP;               // lane quadrants per replica
+    constexpr int UPT = HU / REP;             // hidden units per thread
     static_assert(OW == OP, "obs stride");
+    static_assert(REP == 1 || REP == 2 || REP == 4, "replication factor");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* tW2 = sm + S::OFF_W;
@@ -68,7 +75,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
         mbar_init(bars + 1, 1);
         mbar_fence_init();
     }
-    if (is_mma_warp) umma::tmem_alloc(slot, 128);      // the issuer warp always stays: it also frees the columns
+    if (is_mma_warp) umma::tmem_alloc(slot, 128);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -82,16 +89,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
     }
     const uint32_t tmem = *slot;
     mbar_wait(bars, 0);
-    // `rows` (32, 64 or 128) environments per CTA: with few environments the per-step latency, not the throughput, sets
-    // the pace, so they are spread over more CTAs and the warps of the unused row windows leave.
-    const uint32_t nthr = (uint32_t)(rows / 32) * 4u * 32u + 32u;      // participants of the issuer hand-off barrier
-    if (!is_mma_warp && (warp & 3) * 32 >= rows) return;
 
     if (is_mma_warp) {
         const uint32_t aW2 = smem_u32(tW2), aH1 = smem_u32(tH1);
         constexpr uint32_t ID_FWD = umma::make_idesc(128, 64, false, false);
         for (int t = 0; t <= T; ++t) {
-            named_bar_sync(RB_FWD, nthr);
+            named_bar_sync(RB_FWD, TC_THREADS);
             umma::fence_after_sync();
             if (umma::elect_one()) {
 #pragma unroll
@@ -111,17 +114,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
     }
 
     // =========================== compute warps ===========================
-    const int rw = warp & 3, half = (warp >> 2) & 1, net = (warp >> 3) & 1;
-    const int r = rw * 32 + lane;
-    const int u0 = half * HU;
-    const uint32_t trow = tmem + ((uint32_t)(rw * 32) << 16);
+    const int q = warp & 3, half = (warp >> 2) & 1, net = (warp >> 3) & 1;
+    const int grp = q % QG, replica = q / QG;
+    const int er = grp * 32 + lane;                             // env row inside the CTA
+    const int u0 = half * HU + replica * UPT;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);    // this warp's TMEM lane quadrant
     const int wrow0 = net == 0 ? 0 : A;
     const int nheads = net == 0 ? A : 1;
-    const bool owner_warp = warp < 4;                         // actor, first half: owns the env state
+    const bool owner_warp = net == 0 && half == 0 && replica == 0;   // owns the env state
     const int N = env.num_envs;
-    const int n = blockIdx.x * rows + r;
+    const int n = blockIdx.x * ROWS + er;
     const bool own = owner_warp && n < N;
     const uint32_t gid = env.env_gid0 + (uint32_t)n;
+    constexpr int NSLOT = 2 * REP;                              // head partial sums per env and output
 
     EnvLane e;
     e.s[0] = e.s[1] = e.s[2] = e.s[3] = 0.0; e.elapsed = 0; e.ep_ret = 0.0f; e.ep_len = 0;
@@ -137,27 +142,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
                 env_observation<KIND>(e.s, obs);
                 float4* o4 = reinterpret_cast<float4*>(buf.obs + ((size_t)t * N + n) * OP);
 #pragma unroll
-                for (int q = 0; q < OP / 4; ++q) o4[q] = make_float4(obs[4 * q], obs[4 * q + 1], obs[4 * q + 2], obs[4 * q + 3]);
+                for (int qq = 0; qq < OP / 4; ++qq) o4[qq] = make_float4(obs[4 * qq], obs[4 * qq + 1], obs[4 * qq + 2], obs[4 * qq + 3]);
             }
 #pragma unroll
-            for (int q = 0; q < OP / 4; ++q)
-                *reinterpret_cast<float4*>(obs_s + r * OW + 4 * q) = make_float4(obs[4 * q], obs[4 * q + 1], obs[4 * q + 2], obs[4 * q + 3]);
+            for (int qq = 0; qq < OP / 4; ++qq)
+                *reinterpret_cast<float4*>(obs_s + er * OW + 4 * qq) = make_float4(obs[4 * qq], obs[4 * qq + 1], obs[4 * qq + 2], obs[4 * qq + 3]);
         }
-        named_bar_sync(RB_ROW0 + rw, 128);
+        named_bar_sync(RB_ROW0 + grp, 128 * REP);
 
-        // ---- S1: layer 1 (32 units of this thread's net) -> bf16 tile, hand the forward GEMM ----
+        // ---- S1: layer 1 (UPT units of this thread's net) -> bf16 tile rows of every replica, hand the forward GEMM ----
         {
             float x[OW];
 #pragma unroll
-            for (int q = 0; q < OW / 4; ++q) {
-                const float4 v4 = *reinterpret_cast<const float4*>(obs_s + r * OW + 4 * q);
-                x[4 * q] = v4.x; x[4 * q + 1] = v4.y; x[4 * q + 2] = v4.z; x[4 * q + 3] = v4.w;
+            for (int qq = 0; qq < OW / 4; ++qq) {
+                const float4 v4 = *reinterpret_cast<const float4*>(obs_s + er * OW + 4 * qq);
+                x[4 * qq] = v4.x; x[4 * qq + 1] = v4.y; x[4 * qq + 2] = v4.z; x[4 * qq + 3] = v4.w;
             }
-            float h[HU];
+            float h[UPT];
             const float* w1 = sW1 + (net * H + u0) * OW;
             const float* b1 = sB1 + net * H + u0;
 #pragma unroll
-            for (int k4 = 0; k4 < HU / 4; ++k4) {
+            for (int k4 = 0; k4 < UPT / 4; ++k4) {
                 const float4 bb = *reinterpret_cast<const float4*>(b1 + 4 * k4);
                 const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -165,28 +170,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
                     const int kk = 4 * k4 + j;
                     float z = bv[j];
 #pragma unroll
-                    for (int q = 0; q < OW / 4; ++q) {
-                        const float4 w = *reinterpret_cast<const float4*>(w1 + kk * OW + 4 * q);
-                        z = fmaf(x[4 * q + 3], w.w, fmaf(x[4 * q + 2], w.z, fmaf(x[4 * q + 1], w.y, fmaf(x[4 * q], w.x, z))));
+                    for (int qq = 0; qq < OW / 4; ++qq) {
+                        const float4 w = *reinterpret_cast<const float4*>(w1 + kk * OW + 4 * qq);
+                        z = fmaf(x[4 * qq + 3], w.w, fmaf(x[4 * qq + 2], w.z, fmaf(x[4 * qq + 1], w.y, fmaf(x[4 * qq], w.x, z))));
                     }
                     h[kk] = tanh_mufu(z);
                 }
             }
-            store_half_row_sw128(tH1 + net * 16384, r, half * 4, h);
+            uint4 ch[UPT / 8];
+#pragma unroll
+            for (int c = 0; c < UPT / 8; ++c) {
+                ch[c].x = umma::pack_bf16(h[8 * c + 0], h[8 * c + 1]);
+                ch[c].y = umma::pack_bf16(h[8 * c + 2], h[8 * c + 3]);
+                ch[c].z = umma::pack_bf16(h[8 * c + 4], h[8 * c + 5]);
+                ch[c].w = umma::pack_bf16(h[8 * c + 6], h[8 * c + 7]);
+            }
+#pragma unroll
+            for (int rp = 0; rp < REP; ++rp) {      // the GEMM row of every replica of this env needs all 64 units
+                const int row = (rp * QG + grp) * 32 + lane;
+#pragma unroll
+                for (int c = 0; c < UPT / 8; ++c)
+                    *reinterpret_cast<uint4*>(tH1 + net * 16384 + umma::sw128_off(row, u0 / 8 + c)) = ch[c];
+            }
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
-        named_bar_arrive(RB_FWD, nthr);
+        named_bar_arrive(RB_FWD, TC_THREADS);
 
         // ---- S2: layer-2 epilogue and partial head dot products ----
         mbar_wait(bars + 1, (uint32_t)t & 1u);
         umma::fence_after_sync();
         {
-            float h[HU];
-            umma::ld32(trow + net * 64 + u0, h);
+            float h[UPT];
+            umma::ldn<UPT>(trow + net * 64 + u0, h);
             const float* b2 = sB2 + net * H + u0;
 #pragma unroll
-            for (int k4 = 0; k4 < HU / 4; ++k4) {
+            for (int k4 = 0; k4 < UPT / 4; ++k4) {
                 const float4 bb = *reinterpret_cast<const float4*>(b2 + 4 * k4);
                 h[4 * k4 + 0] = tanh_mufu(h[4 * k4 + 0] + bb.x);
                 h[4 * k4 + 1] = tanh_mufu(h[4 * k4 + 1] + bb.y);
@@ -199,30 +218,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
                     const float* w = sW4 + (wrow0 + a) * H + u0;
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                    for (int k4 = 0; k4 < HU / 4; ++k4) {
+                    for (int k4 = 0; k4 < UPT / 4; ++k4) {
                         const float4 ww = *reinterpret_cast<const float4*>(w + 4 * k4);
                         s0 = fmaf(h[4 * k4 + 0], ww.x, s0);
                         s1 = fmaf(h[4 * k4 + 1], ww.y, s1);
                         s2 = fmaf(h[4 * k4 + 2], ww.z, s2);
                         s3 = fmaf(h[4 * k4 + 3], ww.w, s3);
                     }
-                    // slots: actor half h -> h*A + a (a < A <= 3), critic half h -> 6 + h
-                    const int sl = net == 0 ? half * A + a : 6 + half;
-                    xch[sl * TC_TILE + r] = (s0 + s1) + (s2 + s3);
+                    // slots: actor output a, part j = half*REP + replica -> j*A + a; critic part j -> NSLOT*A + j
+                    const int j = half * REP + replica;
+                    const int sl = net == 0 ? j * A + a : NSLOT * A + j;
+                    xch[sl * TC_TILE + er] = (s0 + s1) + (s2 + s3);
                 }
             }
         }
         umma::fence_before_sync();
-        named_bar_sync(RB_ROW0 + rw, 128);
+        named_bar_sync(RB_ROW0 + grp, 128 * REP);
 
         // ---- S3: owners: value store, sample, env step ----
         if (own) {
             const size_t i0 = (size_t)t * N + n;
-            buf.val[i0] = (xch[6 * TC_TILE + r] + xch[7 * TC_TILE + r]) + sB4[A];
+            float v = xch[(NSLOT * A) * TC_TILE + er];
+#pragma unroll
+            for (int j = 1; j < NSLOT; ++j) v += xch[(NSLOT * A + j) * TC_TILE + er];
+            buf.val[i0] = v + sB4[A];
             if (t < T) {
                 float l[A];
 #pragma unroll
-                for (int a = 0; a < A; ++a) l[a] = (xch[a * TC_TILE + r] + xch[(A + a) * TC_TILE + r]) + sB4[a];
+                for (int a = 0; a < A; ++a) {
+                    float sacc = xch[a * TC_TILE + er];
+#pragma unroll
+                    for (int j = 1; j < NSLOT; ++j) sacc += xch[(j * A + a) * TC_TILE + er];
+                    l[a] = sacc + sB4[a];
+                }
                 const uint64_t step = step0 + (uint64_t)t;
                 const uint4 rr = philox_seeded(env.seed, gid, (uint32_t)step, (uint32_t)(step >> 32), TAG_ACTION);
                 float lp;
@@ -241,23 +269,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
     __syncthreads();
 }
 
+template <int KIND, int REP>
+static int launch_rollout_tc_rep(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
+                                 const drl_ep_log_t& log, cudaStream_t st) {
+    using SP = EnvSpec<KIND>;
+    const int smem = RoTcSmem<SP::O, SP::A>::TOTAL;
+    DRL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<KIND, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    constexpr int ROWS = TC_TILE / REP;
+    const int blocks = (env.num_envs + ROWS - 1) / ROWS;
+    rollout_tc_kernel<KIND, REP><<<blocks, TC_THREADS, smem, st>>>(env, packed, T, step0, buf, log);
+    DRL_LAUNCH_CHECK("rollout_tc_kernel");
+    return DRL_OK;
+}
+
 template <int KIND>
 static int launch_rollout_tc_kind(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
                                   const drl_ep_log_t& log, cudaStream_t st) {
-    using SP = EnvSpec<KIND>;
-    const int smem = RoTcSmem<SP::O, SP::A>::TOTAL;
-    DRL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    // envs per CTA: 128 when that fills the GPU, otherwise fewer rows per CTA over more CTAs (latency-bound regime)
+    // envs per CTA: 128 when that fills the GPU, otherwise fewer envs per CTA over more CTAs, each env spread over 2 or 4
+    // GEMM rows (latency-bound regime)
     const int sms = sm_count();
     int rows = 128;
     if ((env.num_envs + 127) / 128 < sms) rows = (env.num_envs + 63) / 64 <= sms ? 64 : 128;
     if ((env.num_envs + 63) / 64 < sms && (env.num_envs + 31) / 32 <= sms) rows = 32;
     const char* ov = getenv("DRL_ROLLOUT_ROWS");
     if (ov) { const int v = atoi(ov); if (v == 32 || v == 64 || v == 128) rows = v; }
-    const int blocks = (env.num_envs + rows - 1) / rows;
-    rollout_tc_kernel<KIND><<<blocks, TC_THREADS, smem, st>>>(env, packed, T, step0, buf, log, rows);
-    DRL_LAUNCH_CHECK("rollout_tc_kernel");
-    return DRL_OK;
+    if (rows == 32) return launch_rollout_tc_rep<KIND, 4>(env, packed, T, step0, buf, log, st);
+    if (rows == 64) return launch_rollout_tc_rep<KIND, 2>(env, packed, T, step0, buf, log, st);
+    return launch_rollout_tc_rep<KIND, 1>(env, packed, T, step0, buf, log, st);
 }
 
 int launch_rollout_tc(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,

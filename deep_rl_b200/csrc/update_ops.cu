@@ -645,7 +645,7 @@ static int minibatch_update_impl(const drl_net_t* net, float* packed, const floa
         fill_adam(g.tail.a, net, params, grad_out, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_grad_norm, 1.0 / world, packed,
                   norm_out);
         g.tail.grad_out = grad_out; g.tail.loss_terms_out = loss_terms_out;
-        g.tail.cta_sumsq = reinterpret_cast<double*>((char*)workspace + w.stat_partials);
+        g.tail.cta_sumsq = reinterpret_cast<double*>((char*)workspace + w.cta_sumsq);
         g.tail.ctr = reinterpret_cast<uint32_t*>((char*)workspace + w.counters) + 8;
         g.tail.world = world; g.tail.rank = comm ? comm->rank : 0; g.tail.seq = comm ? comm->seq : 0;
         g.tail.error_flag = comm ? comm->error_flag : nullptr;
@@ -660,11 +660,12 @@ static int minibatch_update_impl(const drl_net_t* net, float* packed, const floa
     FusedArgs f;
     fill_adam(f.a, net, params, grad_out, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_grad_norm, 1.0, packed, norm_out);
     f.grad_part = g.grad_part; f.loss_part = g.loss_part; f.grad_out = grad_out; f.loss_terms_out = loss_terms_out;
-    f.cta_sumsq = reinterpret_cast<double*>((char*)workspace + w.stat_partials);     // free between statistics launches
+    f.cta_sumsq = reinterpret_cast<double*>((char*)workspace + w.cta_sumsq);
     f.arrive = reinterpret_cast<uint32_t*>((char*)workspace + w.counters) + 4;
     f.depart = f.arrive + 1;
     f.nparts = grid; f.ppad = g.ppad; f.mb_count = mb_count; f.ent_coef = coef->ent_coef; f.vf_coef = coef->vf_coef;
     const int blocks = (f.a.P + 31) / 32;
+    DRL_REQUIRE(blocks <= 1024, "drl_ppo_minibatch_update: %d parameters exceed the squared-norm scratch", f.a.P);
     void* args[] = {&f};
     const void* fn = net->obs_dim == 4 ? (const void*)reduce_clip_adam_kernel<4, 2> : (const void*)reduce_clip_adam_kernel<6, 3>;
     DRL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(32, 8), args, 0, st));

@@ -231,3 +231,23 @@ def test_train_prints_reference_format(capsys):
     assert all(re.fullmatch(r"global_step=\d+, episodic_return=\d+\.\d\d", ln) for ln in out)
     steps = [int(ln.split(",")[0].split("=")[1]) for ln in out]
     assert steps == sorted(steps) and steps[-1] < 1024
+
+
+@pytest.mark.parametrize("env_id,N,T,prec", [("Acrobot-v1", 24, 64, "fp32"), ("CartPole-v1", 64, 32, "bf16")])
+def test_side_stream_overlap_is_bit_identical(env_id, N, T, prec):
+    """Permutations / statistics scheduled on the side stream must not change a single bit of the result (and the result
+    must be the same run after run: the kernels have no atomics on the data path)."""
+    import deep_rl_b200 as drl
+    ref = None
+    for overlap in (False, True):
+        for _rep in range(6):
+            cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=2, total_timesteps=N * T * 10, update_precision=prec,
+                                overlap_streams=overlap)
+            tr = drl.PPOTrainer(cfg)
+            for _ in range(3):
+                tr.update(10)
+            torch.cuda.synchronize()
+            got = (tr.agent.flat_params.cpu().numpy().copy(), tr.loss_terms.cpu().numpy().copy())
+            if ref is None:
+                ref = got
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), f"overlap={overlap}"
