@@ -50,7 +50,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src: str):
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        extra = os.environ.get("DRL_EXTRA_NVCC_FLAGS", "").split()     # e.g. -DDRL_ROLLOUT_STAMPS for profiles/tools/ro_stamps.py
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, res
 

@@ -26,6 +26,13 @@ namespace drl {
 int check_env(const drl_env_t* env);
 drl_ep_log_t log_or_empty(const drl_ep_log_t* log);
 
+// per-step cycle stamps of CTA 0 (owner warp and one other warp), only in a -DDRL_ROLLOUT_STAMPS build (profiles/tools/ro_stamps.py)
+#ifdef DRL_ROLLOUT_STAMPS
+__device__ long long g_ro_dbg[1024];
+#define RO_STAMP(ev) do { if (blockIdx.x == 0 && lane == 0 && t >= 8 && t < 12 && (warp == 0 || warp == 5)) g_ro_dbg[(warp == 0 ? 0 : 512) + (t - 8) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define RO_STAMP(ev) do { } while (0)
+#endif
 enum : uint32_t { RB_FWD = 1, RB_ROW0 = 2 };   // named barriers: issuer hand-off, 4 row-window barriers (2..5)
 
 template <int O, int A>
@@ -134,6 +141,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
 
     for (int t = 0; t <= T; ++t) {
         // ---- S0: observation of the current state ----
+        RO_STAMP(0);
+
         if (owner_warp) {
             float obs[OP];
 #pragma unroll
@@ -148,7 +157,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
             for (int qq = 0; qq < OP / 4; ++qq)
                 *reinterpret_cast<float4*>(obs_s + er * OW + 4 * qq) = make_float4(obs[4 * qq], obs[4 * qq + 1], obs[4 * qq + 2], obs[4 * qq + 3]);
         }
+        RO_STAMP(1);
         named_bar_sync(RB_ROW0 + grp, 128 * REP);
+        RO_STAMP(2);
 
         // ---- S1: layer 1 (UPT units of this thread's net) -> bf16 tile rows of every replica, hand the forward GEMM ----
         {
@@ -193,13 +204,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
                     *reinterpret_cast<uint4*>(tH1 + net * 16384 + umma::sw128_off(row, u0 / 8 + c)) = ch[c];
             }
         }
+        RO_STAMP(3);
         umma::fence_proxy_async();
         umma::fence_before_sync();
         named_bar_arrive(RB_FWD, TC_THREADS);
+        RO_STAMP(4);
 
         // ---- S2: layer-2 epilogue and partial head dot products ----
         mbar_wait(bars + 1, (uint32_t)t & 1u);
         umma::fence_after_sync();
+        RO_STAMP(5);
         {
             float h[UPT];
             umma::ldn<UPT>(trow + net * 64 + u0, h);
@@ -232,8 +246,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
                 }
             }
         }
+        RO_STAMP(6);
         umma::fence_before_sync();
         named_bar_sync(RB_ROW0 + grp, 128 * REP);
+        RO_STAMP(7);
 
         // ---- S3: owners: value store, sample, env step ----
         if (own) {
@@ -251,16 +267,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
                     for (int j = 1; j < NSLOT; ++j) sacc += xch[(j * A + a) * TC_TILE + er];
                     l[a] = sacc + sB4[a];
                 }
+                RO_STAMP(8);
                 const uint64_t step = step0 + (uint64_t)t;
                 const uint4 rr = philox_seeded(env.seed, gid, (uint32_t)step, (uint32_t)(step >> 32), TAG_ACTION);
+                RO_STAMP(9);
                 float lp;
                 const int act = sample_categorical<A>(l, u01_f32(rr.x), lp);
+                RO_STAMP(10);
                 buf.act[i0] = (uint8_t)act;
                 buf.logp[i0] = lp;
                 float reward;
                 const bool done = env_step<KIND>(e, act, reward, env.seed, gid, step, env.max_episode_steps, log);
                 buf.rew[i0 + N] = reward;
                 buf.done[i0 + N] = done ? 1 : 0;
+                RO_STAMP(11);
             }
         }
     }
@@ -305,3 +325,9 @@ int launch_rollout_tc(const drl_env_t& env, const float* packed, int T, uint64_t
 }
 
 }  // namespace drl
+
+#ifdef DRL_ROLLOUT_STAMPS
+extern "C" int drl_debug_rollout_stamps(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, drl::g_ro_dbg, sizeof(long long) * 1024) == cudaSuccess ? 0 : 1;
+}
+#endif
