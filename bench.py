@@ -42,14 +42,53 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled in-process every millisecond (the timed
+    region of the default run is only tens of milliseconds long, too short for `nvidia-smi -lms`), with nvidia-smi as the
+    fallback when pynvml is not importable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.nvml, self.handle, self.stop_flag = None, None, False
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def _nvml_sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            for bit, name in self.BITS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _nvml_loop(self):
+        while not self.stop_flag:
+            try:
+                self._nvml_sample()
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                self.handle = torch.cuda._get_pynvml_handler(self.gpu)      # maps the CUDA ordinal to the NVML device
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -64,6 +103,15 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            try:
+                self._nvml_sample()          # the GPU is still draining the timed work when this is called
+            except Exception:
+                pass
+            self.stop_flag = True
+            self.t.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -82,7 +130,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -184,9 +232,9 @@ def run_b200(args):
         tr.update(nu)
         e1.record()
         evs.append((e0, e1))
+    clocks = sampler.stop() if sampler else None      # last sample while the queued updates are still running
     torch.cuda.synchronize()
     dist.barrier()
-    clocks = sampler.stop() if sampler else None
     launches = tr.kernel_launches - launches0
     phases = tr.phase_ms()
     tr.timing = False
