@@ -134,8 +134,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU implementation (oracle port; /root/reference and gym do not exist
-# on the GPU box), one independent single-threaded process per host core.
+# reference arm: the reference's CPU implementation of the path on THIS arm's configuration.  /root/reference and gym do
+# not exist on the GPU box, so it is the oracle port: the N-env port (oracle/ppo_vector_port.py: batched PyTorch CPU ops on
+# all host threads + the C env/sampler/GAE) on the benchmarked workload, and -- for information -- the faithful single-env
+# port of the script (oracle/ppo_port.py), one process per host core.
 # ------------------------------------------------------------------------------------------------
 def _port_worker(seed: int, updates: int, warm: int, q):
     import torch
@@ -148,36 +150,83 @@ def _port_worker(seed: int, updates: int, warm: int, q):
     q.put((tr.env_steps, time.perf_counter() - t0))
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _single_env_processes(updates: int, warm: int):
+    """One faithful single-env port process per host core -> (env-steps/s summed, processes)."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     procs_n = max(1, min(cores, 64))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    t0 = time.perf_counter()
-    procs = [ctx.Process(target=_port_worker, args=(i + 1, args.steps, args.warmup, q)) for i in range(procs_n)]
+    procs = [ctx.Process(target=_port_worker, args=(i + 1, updates, warm, q)) for i in range(procs_n)]
     for p in procs:
         p.start()
     res = [q.get() for _ in procs]
     for p in procs:
         p.join()
-    wall = time.perf_counter() - t0
-    steps = sum(r[0] for r in res)
-    slowest = max(r[1] for r in res)
-    value = steps / slowest
+    return sum(r[0] for r in res) / max(r[1] for r in res), procs_n
+
+
+def _workload_name(world: int, envs: int, T: int, env_id: str) -> str:
+    if world == 1 and envs == 4096 and T == 128 and env_id == "CartPole-v1":
+        return "C2: PPO CartPole-v1, 4096 envs x 128 steps, 64-wide MLP, 1xB200"
+    if envs == 65_536 and T == 128 and env_id == "CartPole-v1":
+        return f"C3: PPO CartPole-v1, 65,536 envs/GPU x 128 steps env-sharded across {world} B200, NCCL gradient all-reduce"
+    return f"custom: {env_id}, {envs} envs/GPU x {T} steps"
+
+
+def _vector_port_sample(env_id: str, envs: int, T: int, updates: int, warm: int, budget_s: float):
+    """Times `updates` updates of the N-env CPU port on all host threads.  The env count is reduced (power of two) when the
+    full workload would not fit the time budget.  Returns (env-steps/s, seconds per update, envs used, threads)."""
+    import torch
+    from oracle import ppo_vector_port as vp
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    probe_envs = min(envs, 512)
+    probe = vp.VectorPort(env_id, probe_envs, T)
+    probe.update()
+    t0 = time.perf_counter()
+    probe.update()
+    per_env_update = (time.perf_counter() - t0) / probe_envs          # pessimistic: larger batches are more efficient
+    total = updates + max(1, warm)
+    use = envs
+    while use > 256 and per_env_update * use * total > budget_s:
+        use //= 2
+    port = vp.VectorPort(env_id, use, T)
+    for _ in range(max(1, warm)):
+        port.update()
+    secs = []
+    for _ in range(updates):
+        t0 = time.perf_counter()
+        port.update()
+        secs.append(time.perf_counter() - t0)
+    return use * T * updates / sum(secs), sum(secs) / updates, use, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = args.gpus
+    envs = args.envs_per_gpu if args.envs_per_gpu else (4096 if world == 1 else 65_536)
+    T = args.num_steps
+    t_all = time.perf_counter()
+    value, per_update, used, threads = _vector_port_sample(args.env_id, envs, T, args.steps, args.warmup, budget_s=150.0)
+    single, procs_n = _single_env_processes(min(args.steps, 5), 1)
+    wall = time.perf_counter() - t_all
+    B = envs * T
+    sample = (f"{args.steps} updates of the N-env CPU port (oracle/ppo_vector_port.py: batched PyTorch CPU ops + C env/sampler/GAE) with "
+              f"{used} envs x {T} steps on {threads} host threads after {max(1, args.warmup)} warm-up update(s), {per_update:.2f} s per update"
+              + ("" if used == envs else f"; bounded sample: {used} of the {envs} envs per GPU, same per-env-step work")
+              + f"; for information, the faithful single-env port of ppo.py as {procs_n} independent processes: {single:.0f} env-steps/s; wall {wall:.0f}s")
     line = {
         "impl": "reference", "metric": "PPO env-steps/sec (rollout+update) CartPole-v1", "value": value, "unit": "env-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * slowest / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_update,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "reference ppo.py shape: CartPole-v1, 1 env x 128 steps per update, 64-wide MLP, "
-                               f"{procs_n} independent single-threaded processes (the script is single-threaded)",
-                   "env_id": "CartPole-v1", "num_steps": 128, "hidden": 64},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": procs_n, "kind": "port",
-                         "sample": f"{args.steps} updates x 128 env-steps per process after {max(1, args.warmup)} warm-up update(s); "
-                                   f"per-process {value / procs_n:.0f} env-steps/s; host has {cores} cores; wall {wall:.1f}s"},
+        "config": {"workload": _workload_name(world, envs, T, args.env_id), "precision": "fp32 (PyTorch CPU)", "env_id": args.env_id,
+                   "envs_per_gpu": envs, "num_steps": T, "hidden": 64, "minibatch_size": (B + 3) // 4, "update_epochs": 4,
+                   "optimizer_steps_per_update": 16, "parallelism": f"host CPU, {threads} threads (no GPU)"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "single_env_reference_shape": {"value": single, "unit": "env-steps/s", "processes": procs_n},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -200,9 +249,7 @@ def run_b200(args):
 
     envs = args.envs_per_gpu if args.envs_per_gpu else (4096 if world == 1 else 65_536)
     T = args.num_steps
-    workload = ("C2: PPO CartPole-v1, 4096 envs x 128 steps, 64-wide MLP, 1xB200" if (world == 1 and envs == 4096 and T == 128 and args.env_id == "CartPole-v1")
-                else f"C3: PPO CartPole-v1, 65,536 envs/GPU x 128 steps env-sharded across {world} B200, NCCL gradient all-reduce"
-                if (envs == 65_536 and T == 128 and args.env_id == "CartPole-v1") else f"custom: {args.env_id}, {envs} envs/GPU x {T} steps")
+    workload = _workload_name(world, envs, T, args.env_id)
     total_updates = args.warmup + 2 * args.steps + 8
     cfg = PPOConfig(env_id=args.env_id, num_envs=envs, num_steps=T, total_timesteps=envs * T * world * total_updates, seed=1,
                     update_precision=args.precision, grad_allreduce=args.grad_allreduce)
@@ -318,13 +365,19 @@ def run_b200(args):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
+        # the same workload on the host cores: N-env CPU port on all threads (bounded to ~cpu_seconds), plus the faithful
+        # single-env port of the script on one core for information
         from oracle import ppo_port as pp
         import torch as _t
+        v, per_update, used, threads = _vector_port_sample(args.env_id, envs, T, 2, 1, budget_s=args.cpu_seconds)
         _t.set_num_threads(1)
-        r = pp.time_port(args.cpu_seconds)
-        cpu_baseline = {"value": r["steps_per_s"], "unit": "env-steps/s", "cores": 1, "kind": "port",
-                        "sample": f"{r['updates']} updates x 128 env-steps of the single-env CPU port of ppo.py "
-                                  f"({r['seconds']:.1f}s, single-threaded like the reference; host has {os.cpu_count()} cores)"}
+        r = pp.time_port(min(5.0, args.cpu_seconds))
+        cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                        "sample": f"2 updates of the N-env CPU port (oracle/ppo_vector_port.py) with {used} envs x {T} steps on {threads} host "
+                                  f"threads, {per_update:.2f} s per update" + ("" if used == envs else f" (bounded sample of the {envs} envs)")
+                                  + f"; the faithful single-env port of ppo.py on one core: {r['steps_per_s']:.0f} env-steps/s "
+                                  f"({r['updates']} updates x 128 env-steps)",
+                        "single_env_one_core": r["steps_per_s"]}
 
     line = {
         "metric": "PPO env-steps/sec (rollout+update) CartPole-v1", "value": value, "unit": "env-steps/s", "n_gpus": world,

@@ -113,7 +113,7 @@ def minibatch_loss_and_grad(flat_np, obs, act, logp_old, adv, ret, val_old, O, H
     terms = minibatch_loss(flat, t(obs), t(act, torch.int64), t(logp_old), t(adv), t(ret), t(val_old), O, H, A, c,
                            adv_mean, adv_std)
     terms[0].backward()
-    return [float(x) for x in terms], flat.grad.detach().numpy().copy()
+    return [float(x.detach()) for x in terms], flat.grad.detach().numpy().copy()
 
 
 def clip_adam(flat_np, grad_np, m_np, v_np, step: int, lr: float, max_grad_norm: float = 0.5,

@@ -187,3 +187,18 @@ def test_permutation_uniformity():
         p = clib.permutation(B, seed=1, epoch_ctr=e, rank=0)
         slots[int(np.nonzero(p == 0)[0][0]) // 32] += 1
     assert (np.abs(slots / 2000 - 0.25) < 0.04).all()
+
+
+def test_vector_port_is_deterministic_and_learns_something():
+    """The N-env CPU port used as the all-threads CPU arm of bench.py: two runs agree bit for bit, parameters move, the
+    step accounting is N*T per update."""
+    from oracle import ppo_vector_port as vp
+    runs = []
+    for _ in range(2):
+        p = vp.VectorPort("CartPole-v1", num_envs=8, num_steps=16, seed=3)
+        p0 = p.params.copy()
+        out = [p.update(), p.update()]
+        assert p.env_steps == 2 * 8 * 16 and p.adam_step == 32
+        assert np.isfinite(out[-1]["loss"]) and np.abs(p.params - p0).max() > 1e-5
+        runs.append(p.params.copy())
+    assert np.array_equal(runs[0], runs[1])
