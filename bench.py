@@ -298,9 +298,11 @@ def run_b200(args):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         tr.update(nu)
-        m = tr.metrics(with_episode_log=False)   # D2H: loss terms + grad norm (36 B), episode count + sums (24 B)
-        d2h += 36 + 24
-        _ = (m["mean_return"], m["loss"])
+        # D2H every update, like the reference's prints: loss terms + grad norm (36 B), episode count + sums (24 B) and the
+        # (step, env, return, length) record of every finished episode (20 B each, up to the log capacity)
+        m = tr.metrics(with_episode_log="arrays")
+        d2h += 36 + tr.env.log.last_d2h_bytes
+        _ = (m["mean_return"], m["loss"], len(m["episode_log"]["ret"]))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_s = dist.all_reduce_max(e2e_s, dev)
@@ -389,9 +391,9 @@ def run_b200(args):
                                                                                   if tr_peer else ", NCCL gradient all-reduce per minibatch")), "l2": "flushed between updates (256 MiB memset outside the timed events); "
                    "every update regenerates its own rollout data"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / args.steps,
-                "note": "public API PPOTrainer.update()+metrics() with a host sync and a device->host read of the loss terms, "
-                        "gradient norm and episode statistics every update; the environments live on the device, so the "
-                        "only per-update host inputs are kernel arguments (no tensor H2D)"},
+                "note": "public API PPOTrainer.update()+metrics() with host syncs and a device->host read of the loss terms, "
+                        "gradient norm, episode statistics and the per-episode records (what the reference prints) every update; "
+                        "the environments live on the device, so the only per-update host inputs are kernel arguments (no tensor H2D)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "phases_ms_per_update": {k: v["total_ms"] / args.steps for k, v in phases.items()},
         "scaling_reference": scaling_ref,

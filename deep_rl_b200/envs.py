@@ -51,6 +51,22 @@ class EpisodeLog:
     def clear(self):
         self._hdr.zero_()
 
+    def drain_arrays(self):
+        """D2H read + clear without Python-object conversion: (count, sum_ret, sum_len, {"step","env","ret","len"} numpy views
+        of pinned host buffers, unsorted, valid until the next drain).  Two synchronisations: the header, then the entries."""
+        n, sum_ret, sum_len = self.read_header()
+        k = min(n, self.cap)
+        if not hasattr(self, "_host"):
+            self._host = {"step": torch.zeros(self.cap, dtype=torch.int64).pin_memory(), "env": torch.zeros(self.cap, dtype=torch.int32).pin_memory(),
+                          "ret": torch.zeros(self.cap, dtype=torch.float32).pin_memory(), "len": torch.zeros(self.cap, dtype=torch.int32).pin_memory()}
+        if k:
+            for name, src in (("step", self.step), ("env", self.env), ("ret", self.ret), ("len", self.len)):
+                self._host[name][:k].copy_(src[:k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        self.clear()
+        self.last_d2h_bytes = 24 + 20 * k
+        return n, sum_ret, sum_len, {name: buf[:k].numpy() for name, buf in self._host.items()}
+
     def drain(self, with_entries: bool = True):
         """D2H read + clear.  Returns (count, sum_ret, sum_len, entries sorted by (step, env))."""
         n, sum_ret, sum_len = self.read_header()

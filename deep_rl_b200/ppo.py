@@ -314,10 +314,14 @@ class PPOTrainer:
 
     def metrics(self, with_episode_log: bool = True) -> Dict[str, float]:
         """Device->host read of the last update's loss terms, gradient norm and finished-episode statistics
-        (synchronises).  `with_episode_log=False` skips the per-episode entries (40 + 24 bytes are read instead of
-        up to 20 bytes per finished episode)."""
+        (synchronises).  `with_episode_log=False` skips the per-episode entries (36 + 24 bytes are read instead of
+        20 more bytes per finished episode); `"arrays"` returns them as numpy arrays {"step","env","ret","len"} instead of
+        a sorted list of tuples."""
         self._h_terms.copy_(self._d_terms_src(), non_blocking=True)
-        n, sum_ret, sum_len, entries = self.env.log.drain(with_entries=with_episode_log)
+        if with_episode_log == "arrays":     # every finished episode as numpy arrays (no per-entry Python objects)
+            n, sum_ret, sum_len, entries = self.env.log.drain_arrays()
+        else:
+            n, sum_ret, sum_len, entries = self.env.log.drain(with_entries=with_episode_log)
         lt = self._h_terms.tolist()
         if self.peer is not None and int(self.peer.error_flag.item()) != 0:
             raise _lib.DrlError("a peer rank did not arrive at the in-kernel all-reduce within the timeout")
