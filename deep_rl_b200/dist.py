@@ -53,6 +53,23 @@ def all_reduce_sum(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def merge_minibatch_stats(stats: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """Turn rank-local (mean, unbiased std) of minibatches into those of their union over all ranks, in place.
+    stats [..., 2] float32, counts [...] samples per rank-local minibatch.  ONE SUM all-reduce of (n, sum x, sum x^2) in
+    fp64 for all minibatches of the update (global advantage statistics, ppo.py:169 on the global
+    minibatch)."""
+    n = counts.to(torch.float64)
+    mean, std = stats[..., 0].to(torch.float64), stats[..., 1].to(torch.float64)
+    buf = torch.stack([n, mean * n, std * std * (n - 1.0) + n * mean * mean])
+    all_reduce_sum(buf)
+    big_n, s1, s2 = buf[0], buf[1], buf[2]
+    gmean = s1 / big_n
+    gvar = torch.clamp((s2 - s1 * gmean) / (big_n - 1.0), min=0.0)
+    stats[..., 0] = gmean.to(stats.dtype)
+    stats[..., 1] = torch.sqrt(gvar).to(stats.dtype)
+    return stats
+
+
 def all_reduce_max(x: float, device) -> float:
     if td.is_initialized() and td.get_world_size() > 1:
         t = torch.tensor([x], dtype=torch.float64, device=device)

@@ -54,6 +54,8 @@ class PPOConfig:
                                      # the update is bf16 and there are at least 2048 envs
     overlap_streams: bool = True     # permutations (during the rollout) and advantage statistics of later epochs (during the
                                      # minibatch steps of earlier ones) run on a second CUDA stream
+    global_adv_stats: bool = False   # multi-GPU: normalise advantages with the statistics of the GLOBAL minibatch (one extra
+                                     # all-reduce of 3 numbers per minibatch, once per update) instead of per-rank ones
     grad_allreduce: str = "peer"     # multi-GPU gradient exchange: "peer" = one-shot all-reduce over NVLink peer memory inside
                                      # the gradient kernel (bf16 update only), "nccl" = NCCL all-reduce between kernels
     update_precision: str = "bf16"   # "bf16": tcgen05 tensor-core update (bf16 operands, fp32 accumulate); "fp32": CUDA-core update
@@ -131,6 +133,10 @@ class PPOTrainer:
         self._ev_gae = torch.cuda.Event()
         self._ev_stats = [torch.cuda.Event() for _ in range(cfg.update_epochs)]
         self._perms_scheduled = False
+        self._merge_stats = bool(cfg.global_adv_stats and self.world > 1 and torch.distributed.is_available()
+                                 and torch.distributed.is_initialized())
+        M_ = cfg.minibatch_size
+        self._mb_counts = torch.tensor([[min(M_, B - k * M_) for k in range(self.n_mb)]] * cfg.update_epochs, dtype=torch.float64, device=dev)
         P = agent.flat_params.numel()
         self.grad = torch.zeros(P, dtype=f32, device=dev)
         self.exp_avg = torch.zeros(P, dtype=f32, device=dev)
@@ -239,8 +245,13 @@ class PPOTrainer:
                         _lib.check(self.L.drl_adv_stats(net, self.records.data_ptr(), self.idx[epoch].data_ptr(), B, M,
                                                         self.adv_stats[epoch].data_ptr(), self.workspace.data_ptr(),
                                                         self.ws_bytes, st))
-                if self.side is not None:
+                if self.side is not None and not self._merge_stats:
                     self._ev_stats[epoch].record()
+            if self._merge_stats:     # all epochs' statistics first, then one exchange for the whole update
+                _dist.merge_minibatch_stats(self.adv_stats, self._mb_counts)
+                if self.side is not None:
+                    for ev in self._ev_stats:
+                        ev.record()
         self.kernel_launches += cfg.update_epochs
 
     def optimize(self, lr: float) -> None:

@@ -145,6 +145,12 @@ np.testing.assert_allclose(g_avg, g_full, rtol=1e-5, atol=1e-7)
 p1, _, _, norm = po.clip_adam(params, g_avg, np.zeros_like(params), np.zeros_like(params), 1, 2.5e-4)
 t = torch.tensor(p1); dist.all_reduce_sum(t)
 np.testing.assert_allclose(t.numpy() / world, p1, rtol=0, atol=1e-7)     # ranks stay in lock-step
+# global advantage statistics: rank-local (mean, std) of two minibatches merged over ranks == statistics of the union
+xs = [rng.normal(loc=0.3 * k, scale=1.0 + k, size=(world, 40 + 8 * k)).astype(np.float32) for k in range(2)]
+st = torch.tensor([[float(x[rank].mean()), float(x[rank].std(ddof=1))] for x in xs], dtype=torch.float32)
+dist.merge_minibatch_stats(st, torch.tensor([x.shape[1] for x in xs]))
+want = np.array([[x.reshape(-1).mean(), x.reshape(-1).std(ddof=1)] for x in xs])
+np.testing.assert_allclose(st.numpy(), want, rtol=2e-6, atol=1e-7)
 assert dist.all_reduce_max(float(rank), "cpu") == 1.0
 dist.barrier(); dist.shutdown()
 sys.stdout.write("rank-%d-ok\n" % rank); sys.stdout.flush()
