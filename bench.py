@@ -27,9 +27,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-F_FWD = {("CartPole-v1", 64): 17_792, ("Acrobot-v1", 64): 18_432}   # forward FLOPs per sample
-BYTES_PER_ENV_STEP = {"CartPole-v1": 195, "Acrobot-v1": 235}
-GRAD_BYTES_PER_SAMPLE = {"CartPole-v1": 37, "Acrobot-v1": 45}
+F_FWD = {("CartPole-v1", 64): 17_792, ("Acrobot-v1", 64): 18_432, ("MountainCar-v0", 64): 17_408}   # forward FLOPs per sample
+BYTES_PER_ENV_STEP = {"CartPole-v1": 195, "Acrobot-v1": 235, "MountainCar-v0": 155}
+GRAD_BYTES_PER_SAMPLE = {"CartPole-v1": 37, "Acrobot-v1": 45, "MountainCar-v0": 29}
 
 
 def load_peaks():

@@ -37,8 +37,9 @@ int check_net(const drl_net_t* net) {
     if (net->hidden != H) { set_error("hidden=%d unsupported (this build: %d)", net->hidden, H); return DRL_ERR_UNSUPPORTED; }
     const bool cart = net->obs_dim == 4 && net->num_actions == 2 && net->obs_stride == 4;
     const bool acro = net->obs_dim == 6 && net->num_actions == 3 && net->obs_stride == 8;
-    if (!cart && !acro) {
-        set_error("unsupported net shape O=%d A=%d OP=%d (CartPole 4/2/4 or Acrobot 6/3/8)", net->obs_dim,
+    const bool mcar = net->obs_dim == 2 && net->num_actions == 3 && net->obs_stride == 4;
+    if (!cart && !acro && !mcar) {
+        set_error("unsupported net shape O=%d A=%d OP=%d (CartPole 4/2/4, Acrobot 6/3/8 or MountainCar 2/3/4)", net->obs_dim,
                   net->num_actions, net->obs_stride);
         return DRL_ERR_UNSUPPORTED;
     }
@@ -60,17 +61,17 @@ extern "C" {
 int drl_abi_version(void) { return DRL_ABI_VERSION; }
 const char* drl_last_error(void) { return g_err; }
 
-int drl_env_obs_dim(int32_t kind) { return kind == DRL_ENV_CARTPOLE ? 4 : kind == DRL_ENV_ACROBOT ? 6 : DRL_ERR_ARG; }
-int drl_env_num_actions(int32_t kind) { return kind == DRL_ENV_CARTPOLE ? 2 : kind == DRL_ENV_ACROBOT ? 3 : DRL_ERR_ARG; }
-int drl_env_obs_stride(int32_t kind) { return kind == DRL_ENV_CARTPOLE ? 4 : kind == DRL_ENV_ACROBOT ? 8 : DRL_ERR_ARG; }
+int drl_env_obs_dim(int32_t kind) { return kind == DRL_ENV_CARTPOLE ? 4 : kind == DRL_ENV_ACROBOT ? 6 : kind == DRL_ENV_MOUNTAINCAR ? 2 : DRL_ERR_ARG; }
+int drl_env_num_actions(int32_t kind) { return kind == DRL_ENV_CARTPOLE ? 2 : (kind == DRL_ENV_ACROBOT || kind == DRL_ENV_MOUNTAINCAR) ? 3 : DRL_ERR_ARG; }
+int drl_env_obs_stride(int32_t kind) { return (kind == DRL_ENV_CARTPOLE || kind == DRL_ENV_MOUNTAINCAR) ? 4 : kind == DRL_ENV_ACROBOT ? 8 : DRL_ERR_ARG; }
 
 int64_t drl_param_count(const drl_net_t* net) {
     if (check_net(net) != DRL_OK) return -1;
-    return net->obs_dim == 4 ? Packed<4, 2>::C_ALL : Packed<6, 3>::C_ALL;
+    return net->obs_dim == 4 ? Packed<4, 2>::C_ALL : net->obs_dim == 6 ? Packed<6, 3>::C_ALL : Packed<2, 3>::C_ALL;
 }
 int64_t drl_packed_count(const drl_net_t* net) {
     if (check_net(net) != DRL_OK) return -1;
-    return net->obs_dim == 4 ? Packed<4, 2>::TOTAL : Packed<6, 3>::TOTAL;
+    return net->obs_dim == 4 ? Packed<4, 2>::TOTAL : net->obs_dim == 6 ? Packed<6, 3>::TOTAL : Packed<2, 3>::TOTAL;
 }
 int drl_record_width(const drl_net_t* net) {
     if (check_net(net) != DRL_OK) return -1;
@@ -88,7 +89,8 @@ int drl_pack_params(const drl_net_t* net, const float* params, float* packed_out
     const int P = (int)drl_param_count(net);
     const int blocks = (P + 255) / 256;
     if (net->obs_dim == 4) pack_params_kernel<4, 2><<<blocks, 256, 0, as_stream(stream)>>>(params, packed_out);
-    else pack_params_kernel<6, 3><<<blocks, 256, 0, as_stream(stream)>>>(params, packed_out);
+    else if (net->obs_dim == 6) pack_params_kernel<6, 3><<<blocks, 256, 0, as_stream(stream)>>>(params, packed_out);
+    else pack_params_kernel<2, 3><<<blocks, 256, 0, as_stream(stream)>>>(params, packed_out);
     DRL_LAUNCH_CHECK("pack_params_kernel");
     return DRL_OK;
 }

@@ -10,6 +10,7 @@ namespace drl {
 template <int KIND> struct EnvSpec;
 template <> struct EnvSpec<DRL_ENV_CARTPOLE> { static constexpr int O = 4, A = 2, OP = 4; };
 template <> struct EnvSpec<DRL_ENV_ACROBOT>  { static constexpr int O = 6, A = 3, OP = 8; };
+template <> struct EnvSpec<DRL_ENV_MOUNTAINCAR> { static constexpr int O = 2, A = 3, OP = 4; };
 
 struct EnvLane {          // one environment, held in registers by its owning lane
     double s[4];
@@ -36,6 +37,18 @@ __device__ __forceinline__ bool cartpole_physics(double (&s)[4], int action) {
     th_dot = th_dot + tau * thacc;
     s[0] = x; s[1] = x_dot; s[2] = th; s[3] = th_dot;
     return (x < -x_thr) || (x > x_thr) || (th < -theta_thr) || (th > theta_thr);
+}
+
+// MountainCar-v0 (gym 0.21 mountain_car.py): state (position, velocity) in s[0], s[1]; reward is always -1.  Returns terminated.
+__device__ __forceinline__ bool mountaincar_physics(double (&s)[4], int action) {
+    double position = s[0], velocity = s[1];
+    velocity = velocity + ((double)(action - 1) * 0.001 + cos(3.0 * position) * (-0.0025));
+    velocity = fmin(fmax(velocity, -0.07), 0.07);
+    position = position + velocity;
+    position = fmin(fmax(position, -1.2), 0.6);
+    if (position == -1.2 && velocity < 0.0) velocity = 0.0;
+    s[0] = position; s[1] = velocity;
+    return position >= 0.5 && velocity >= 0.0;
 }
 
 // Acrobot-v1 "book" equations of motion.
@@ -99,6 +112,8 @@ __device__ __forceinline__ void env_observation(const double (&s)[4], float (&ob
     if constexpr (KIND == DRL_ENV_CARTPOLE) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) obs[i] = (float)s[i];
+    } else if constexpr (KIND == DRL_ENV_MOUNTAINCAR) {
+        obs[0] = (float)s[0]; obs[1] = (float)s[1]; obs[2] = 0.0f; obs[3] = 0.0f;
     } else {
         double s1, c1, s2, c2;
         sincos(s[0], &s1, &c1);
@@ -112,6 +127,11 @@ __device__ __forceinline__ void env_observation(const double (&s)[4], float (&ob
 template <int KIND>
 __device__ __forceinline__ void env_reset_state(double (&s)[4], uint64_t seed, uint32_t gid, uint64_t step) {
     uint4 o = philox_seeded(seed, gid, (uint32_t)step, (uint32_t)(step >> 32), TAG_RESET);
+    if constexpr (KIND == DRL_ENV_MOUNTAINCAR) {   // position ~ U(-0.6, -0.4), velocity 0
+        s[0] = -0.6 + 0.2 * u01_f64(o.x);
+        s[1] = 0.0; s[2] = 0.0; s[3] = 0.0;
+        return;
+    }
     const double half = KIND == DRL_ENV_CARTPOLE ? 0.05 : 0.1;
     s[0] = -half + (2.0 * half) * u01_f64(o.x);
     s[1] = -half + (2.0 * half) * u01_f64(o.y);
@@ -125,6 +145,7 @@ __device__ __forceinline__ bool env_step(EnvLane& e, int action, float& reward, 
                                          uint64_t step, int max_episode_steps, const drl_ep_log_t& log) {
     bool term;
     if constexpr (KIND == DRL_ENV_CARTPOLE) { term = cartpole_physics(e.s, action); reward = 1.0f; }
+    else if constexpr (KIND == DRL_ENV_MOUNTAINCAR) { term = mountaincar_physics(e.s, action); reward = -1.0f; }
     else { term = acrobot_physics(e.s, action, reward); }
     e.elapsed += 1;
     bool done = term || (e.elapsed >= max_episode_steps);

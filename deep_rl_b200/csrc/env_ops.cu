@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) env_step_kernel(drl_env_t env, uint64_t s
 
 int check_env(const drl_env_t* env) {
     if (env == nullptr) { set_error("env is NULL"); return DRL_ERR_ARG; }
-    if (env->kind != DRL_ENV_CARTPOLE && env->kind != DRL_ENV_ACROBOT) { set_error("unknown env kind %d", env->kind); return DRL_ERR_ARG; }
+    if (env->kind != DRL_ENV_CARTPOLE && env->kind != DRL_ENV_ACROBOT && env->kind != DRL_ENV_MOUNTAINCAR) { set_error("unknown env kind %d", env->kind); return DRL_ERR_ARG; }
     if (env->num_envs <= 0) { set_error("num_envs=%d", env->num_envs); return DRL_ERR_ARG; }
     if (!env->state || !env->elapsed || !env->ep_ret || !env->ep_len) { set_error("env state pointer is NULL"); return DRL_ERR_ARG; }
     if (env->max_episode_steps <= 0) { set_error("max_episode_steps=%d", env->max_episode_steps); return DRL_ERR_ARG; }
@@ -88,6 +88,7 @@ int drl_env_reset(const drl_env_t* env, float* obs_out, void* stream) {
     DRL_REQUIRE(obs_out, "drl_env_reset: obs_out is NULL");
     const int blocks = (env->num_envs + 255) / 256;
     if (env->kind == DRL_ENV_CARTPOLE) env_reset_kernel<DRL_ENV_CARTPOLE><<<blocks, 256, 0, as_stream(stream)>>>(*env, obs_out);
+    else if (env->kind == DRL_ENV_MOUNTAINCAR) env_reset_kernel<DRL_ENV_MOUNTAINCAR><<<blocks, 256, 0, as_stream(stream)>>>(*env, obs_out);
     else env_reset_kernel<DRL_ENV_ACROBOT><<<blocks, 256, 0, as_stream(stream)>>>(*env, obs_out);
     DRL_LAUNCH_CHECK("env_reset_kernel");
     return DRL_OK;
@@ -99,6 +100,7 @@ int drl_env_observe(const drl_env_t* env, float* obs_out, void* stream) {
     DRL_REQUIRE(obs_out, "drl_env_observe: obs_out is NULL");
     const int blocks = (env->num_envs + 255) / 256;
     if (env->kind == DRL_ENV_CARTPOLE) env_observe_kernel<DRL_ENV_CARTPOLE><<<blocks, 256, 0, as_stream(stream)>>>(*env, obs_out);
+    else if (env->kind == DRL_ENV_MOUNTAINCAR) env_observe_kernel<DRL_ENV_MOUNTAINCAR><<<blocks, 256, 0, as_stream(stream)>>>(*env, obs_out);
     else env_observe_kernel<DRL_ENV_ACROBOT><<<blocks, 256, 0, as_stream(stream)>>>(*env, obs_out);
     DRL_LAUNCH_CHECK("env_observe_kernel");
     return DRL_OK;
@@ -113,6 +115,8 @@ int drl_env_step(const drl_env_t* env, uint64_t step, const int32_t* actions, fl
     const drl_ep_log_t l = log_or_empty(log);
     if (env->kind == DRL_ENV_CARTPOLE)
         env_step_kernel<DRL_ENV_CARTPOLE><<<blocks, 256, 0, as_stream(stream)>>>(*env, step, actions, obs_out, rew_out, done_out, l);
+    else if (env->kind == DRL_ENV_MOUNTAINCAR)
+        env_step_kernel<DRL_ENV_MOUNTAINCAR><<<blocks, 256, 0, as_stream(stream)>>>(*env, step, actions, obs_out, rew_out, done_out, l);
     else
         env_step_kernel<DRL_ENV_ACROBOT><<<blocks, 256, 0, as_stream(stream)>>>(*env, step, actions, obs_out, rew_out, done_out, l);
     DRL_LAUNCH_CHECK("env_step_kernel");

@@ -98,6 +98,7 @@ int drl_policy_forward(const drl_net_t* net, const float* packed, const float* o
     DRL_REQUIRE(packed && obs && logits_out && value_out, "drl_policy_forward: NULL pointer");
     if (n <= 0) return DRL_OK;
     if (net->obs_dim == 4) return launch_forward<4, 2, 4>(packed, obs, n, logits_out, value_out, as_stream(stream));
+    if (net->obs_dim == 2) return launch_forward<2, 3, 4>(packed, obs, n, logits_out, value_out, as_stream(stream));
     return launch_forward<6, 3, 8>(packed, obs, n, logits_out, value_out, as_stream(stream));
 }
 

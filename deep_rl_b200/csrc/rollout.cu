@@ -155,5 +155,6 @@ extern "C" int drl_rollout(const drl_env_t* env, const drl_net_t* net, const flo
     if (flags & DRL_ROLLOUT_TENSOR_CORES) return launch_rollout_tc(*env, packed, T, step0, *buf, l, st);
     const int epw = pick_envs_per_warp(env->num_envs);
     if (env->kind == DRL_ENV_CARTPOLE) return dispatch_rollout<DRL_ENV_CARTPOLE>(epw, *env, packed, T, step0, *buf, l, st);
+    if (env->kind == DRL_ENV_MOUNTAINCAR) return dispatch_rollout<DRL_ENV_MOUNTAINCAR>(epw, *env, packed, T, step0, *buf, l, st);
     return dispatch_rollout<DRL_ENV_ACROBOT>(epw, *env, packed, T, step0, *buf, l, st);
 }

@@ -321,6 +321,7 @@ static int launch_rollout_tc_kind(const drl_env_t& env, const float* packed, int
 int launch_rollout_tc(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
                       const drl_ep_log_t& log, cudaStream_t st) {
     if (env.kind == DRL_ENV_CARTPOLE) return launch_rollout_tc_kind<DRL_ENV_CARTPOLE>(env, packed, T, step0, buf, log, st);
+    if (env.kind == DRL_ENV_MOUNTAINCAR) return launch_rollout_tc_kind<DRL_ENV_MOUNTAINCAR>(env, packed, T, step0, buf, log, st);
     return launch_rollout_tc_kind<DRL_ENV_ACROBOT>(env, packed, T, step0, buf, log, st);
 }
 

@@ -597,6 +597,7 @@ static int run_grad(const drl_net_t* net, const float* packed, const float* rec,
     if (g_out) { *g_out = g; if (grid_out == nullptr) return DRL_OK; }   // arguments only
     if (flags & DRL_GRAD_TENSOR_CORES) return launch_grad_tc(net, g, P, grad_out, loss_terms_out, st, grid_out);
     if (net->obs_dim == 4) return launch_grad<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, st, grid_out);
+    if (net->obs_dim == 2) return launch_grad<2, 3, 4, 8>(g, P, grad_out, loss_terms_out, st, grid_out);
     return launch_grad<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, st, grid_out);
 }
 
@@ -667,7 +668,8 @@ static int minibatch_update_impl(const drl_net_t* net, float* packed, const floa
     const int blocks = (f.a.P + 31) / 32;
     DRL_REQUIRE(blocks <= 1024, "drl_ppo_minibatch_update: %d parameters exceed the squared-norm scratch", f.a.P);
     void* args[] = {&f};
-    const void* fn = net->obs_dim == 4 ? (const void*)reduce_clip_adam_kernel<4, 2> : (const void*)reduce_clip_adam_kernel<6, 3>;
+    const void* fn = net->obs_dim == 4 ? (const void*)reduce_clip_adam_kernel<4, 2>
+                     : net->obs_dim == 2 ? (const void*)reduce_clip_adam_kernel<2, 3> : (const void*)reduce_clip_adam_kernel<6, 3>;
     DRL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(32, 8), args, 0, st));
     return DRL_OK;
 }
@@ -741,6 +743,7 @@ int drl_clip_adam(const drl_net_t* net, float* params, const float* grad, float*
     fill_adam(a, net, params, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_grad_norm, grad_scale, packed_out, norm_out);
     const int blocks = (a.P + 255) / 256;
     if (net->obs_dim == 4) clip_adam_kernel<4, 2><<<blocks, 256, 0, as_stream(stream)>>>(a);
+    else if (net->obs_dim == 2) clip_adam_kernel<2, 3><<<blocks, 256, 0, as_stream(stream)>>>(a);
     else clip_adam_kernel<6, 3><<<blocks, 256, 0, as_stream(stream)>>>(a);
     DRL_LAUNCH_CHECK("clip_adam_kernel");
     return DRL_OK;

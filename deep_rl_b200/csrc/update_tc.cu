@@ -774,6 +774,7 @@ static int launch_tc_fused(GradArgs& g, cudaStream_t st) {
 
 int launch_grad_tc_fused(const drl_net_t* net, GradArgs& g, cudaStream_t st) {
     if (net->obs_dim == 4) return launch_tc_fused<4, 2, 4, 8>(g, st);
+    if (net->obs_dim == 2) return launch_tc_fused<2, 3, 4, 8>(g, st);
     return launch_tc_fused<6, 3, 8, 16>(g, st);
 }
 
@@ -794,6 +795,7 @@ static int launch_tc(const GradArgs& g, int P, float* grad_out, float* loss_term
 int launch_grad_tc(const drl_net_t* net, const GradArgs& g, int P, float* grad_out, float* loss_terms_out, cudaStream_t st,
                    int* grid_out) {
     if (net->obs_dim == 4) return launch_tc<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, st, grid_out);
+    if (net->obs_dim == 2) return launch_tc<2, 3, 4, 8>(g, P, grad_out, loss_terms_out, st, grid_out);
     return launch_tc<6, 3, 8, 16>(g, P, grad_out, loss_terms_out, st, grid_out);
 }
 

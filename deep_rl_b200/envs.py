@@ -17,8 +17,8 @@ import torch
 
 from . import _lib
 
-ENV_KINDS = {"CartPole-v1": 0, "Acrobot-v1": 1}
-MAX_EPISODE_STEPS = {"CartPole-v1": 500, "Acrobot-v1": 500}
+ENV_KINDS = {"CartPole-v1": 0, "Acrobot-v1": 1, "MountainCar-v0": 2}
+MAX_EPISODE_STEPS = {"CartPole-v1": 500, "Acrobot-v1": 500, "MountainCar-v0": 200}      # TimeLimit of the gym registrations
 
 
 class EpisodeLog:

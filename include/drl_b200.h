@@ -30,7 +30,7 @@ extern "C" {
 
 #define DRL_ABI_VERSION 1
 
-enum { DRL_ENV_CARTPOLE = 0, DRL_ENV_ACROBOT = 1 };
+enum { DRL_ENV_CARTPOLE = 0, DRL_ENV_ACROBOT = 1, DRL_ENV_MOUNTAINCAR = 2 };   /* gym ids CartPole-v1, Acrobot-v1, MountainCar-v0 */
 enum { DRL_OK = 0, DRL_ERR_ARG = -1, DRL_ERR_UNSUPPORTED = -2, DRL_ERR_CUDA = -3 };
 
 /* Batched environment: replaces gym.make + TimeLimit + RecordEpisodeStatistics + TorchWrapper

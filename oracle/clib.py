@@ -14,8 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libdrl_oracle.so")
 
-ENV_CARTPOLE, ENV_ACROBOT = 0, 1
-ENV_KINDS = {"CartPole-v1": ENV_CARTPOLE, "Acrobot-v1": ENV_ACROBOT}
+ENV_CARTPOLE, ENV_ACROBOT, ENV_MOUNTAINCAR = 0, 1, 2
+ENV_KINDS = {"CartPole-v1": ENV_CARTPOLE, "Acrobot-v1": ENV_ACROBOT, "MountainCar-v0": ENV_MOUNTAINCAR}
+MAX_EPISODE_STEPS = {"CartPole-v1": 500, "Acrobot-v1": 500, "MountainCar-v0": 200}
 UINT64_MAX = (1 << 64) - 1
 
 
@@ -52,6 +53,8 @@ def lib() -> C.CDLL:
         L.drl_or_cartpole_step.restype = C.c_int32
         L.drl_or_acrobot_step.argtypes = [f64p, C.c_int32, f64p]
         L.drl_or_acrobot_step.restype = C.c_int32
+        L.drl_or_mountaincar_step.argtypes = [f64p, C.c_int32]
+        L.drl_or_mountaincar_step.restype = C.c_int32
         L.drl_or_obs_dim.argtypes = [C.c_int32]
         L.drl_or_obs_dim.restype = C.c_int32
         L.drl_or_num_actions.argtypes = [C.c_int32]
@@ -115,6 +118,13 @@ def acrobot_step(state: np.ndarray, action: int):
     return s, float(r.value), bool(term)
 
 
+def mountaincar_step(state: np.ndarray, action: int):
+    s = np.zeros(4, dtype=np.float64)
+    s[:2] = np.asarray(state, dtype=np.float64)[:2]
+    term = lib().drl_or_mountaincar_step(_p(s, C.c_double), int(action))
+    return s[:2].copy(), bool(term)
+
+
 def gae(rew: np.ndarray, done: np.ndarray, val: np.ndarray, gamma: float, lam: float):
     """rew/done/val [T+1, N] float32 (one-slot shift, ppo.py:93-98) -> adv, ret [T+1, N]."""
     rew = np.ascontiguousarray(rew, dtype=np.float32)
@@ -131,8 +141,9 @@ def gae(rew: np.ndarray, done: np.ndarray, val: np.ndarray, gamma: float, lam: f
 class OracleVecEnv:
     """N independent envs with the wrapper chain of ppo.py:79 and auto-reset of ppo.py:127-129."""
 
-    def __init__(self, env_id: str, num_envs: int, seed: int, env_gid0: int = 0, max_episode_steps: int = 500):
+    def __init__(self, env_id: str, num_envs: int, seed: int, env_gid0: int = 0, max_episode_steps: int = 0):
         self.kind = ENV_KINDS[env_id]
+        max_episode_steps = max_episode_steps or MAX_EPISODE_STEPS[env_id]      # TimeLimit of the gym registration
         self.n = int(num_envs)
         self.seed = int(seed)
         self.gid0 = int(env_gid0)

@@ -45,6 +45,8 @@ def test_shape_queries_and_error_codes():
     lib = L.lib()
     assert (lib.drl_env_obs_dim(0), lib.drl_env_num_actions(0), lib.drl_env_obs_stride(0)) == (4, 2, 4)
     assert (lib.drl_env_obs_dim(1), lib.drl_env_num_actions(1), lib.drl_env_obs_stride(1)) == (6, 3, 8)
+    assert (lib.drl_env_obs_dim(2), lib.drl_env_num_actions(2), lib.drl_env_obs_stride(2)) == (2, 3, 4)      # MountainCar-v0
+    assert lib.drl_param_count(C.byref(L.NetT(2, 64, 3, 4))) == 8964
     cart, acro = L.NetT(4, 64, 2, 4), L.NetT(6, 64, 3, 8)
     assert lib.drl_param_count(C.byref(cart)) == 9155
     assert lib.drl_param_count(C.byref(acro)) == 9476

@@ -88,9 +88,9 @@ def _action_seq(kind, n, steps, A):
     return seqs
 
 
-@pytest.mark.parametrize("env_id", ["CartPole-v1", "Acrobot-v1"])
+@pytest.mark.parametrize("env_id", ["CartPole-v1", "Acrobot-v1", "MountainCar-v0"])
 def test_env_step_free_running_vs_oracle(env_id):
-    """>= 600 steps on fixed action sequences (crosses the 500-step TimeLimit), auto-reset included.
+    """>= 600 steps on fixed action sequences (crosses the 500-step TimeLimit; 200 for MountainCar), auto-reset included.
     CartPole runs free for all 640 steps.  Acrobot is a chaotic double pendulum (1-ulp sin/cos differences grow
     exponentially), so its float64 state is re-synchronised from the oracle every 64 steps; the per-step bar of
     1e-6 is unchanged."""

@@ -89,12 +89,15 @@ def _check_rollout(env_id, N, T, seed, sub=None, rounds=2, tc=False):
     ("Acrobot-v1", 40, 48, None),
     ("Acrobot-v1", 70, 24, 32),
     ("Acrobot-v1", 50, 24, 8),
+    ("MountainCar-v0", 45, 40, None),
+    ("MountainCar-v0", 64, 24, 16),
 ])
 def test_rollout_vs_oracle(env_id, N, T, sub):
     _check_rollout(env_id, N, T, seed=3, sub=sub)
 
 
-@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 300, 24), ("CartPole-v1", 128, 40), ("CartPole-v1", 1, 16), ("Acrobot-v1", 130, 16)])
+@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 300, 24), ("CartPole-v1", 128, 40), ("CartPole-v1", 1, 16), ("Acrobot-v1", 130, 16),
+                                       ("MountainCar-v0", 96, 24)])
 def test_tensor_core_rollout_vs_oracle(env_id, N, T):
     _check_rollout(env_id, N, T, seed=3, tc=True)
 
@@ -137,7 +140,7 @@ def _oracle_update(tr, nu):
     return obs, act, logp, val[:T].reshape(B), adv, ret, B, M
 
 
-@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 1, 128), ("CartPole-v1", 64, 32), ("Acrobot-v1", 24, 64)])
+@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 1, 128), ("CartPole-v1", 64, 32), ("Acrobot-v1", 24, 64), ("MountainCar-v0", 32, 48)])
 def test_full_update_vs_oracle(env_id, N, T):
     """rollout (GPU) -> [GAE, permutation, statistics, 16 x (loss+backward, clip, Adam)] on GPU vs the CPU oracle
     fed the same rollout buffers."""
@@ -173,7 +176,7 @@ def test_full_update_vs_oracle(env_id, N, T):
     assert np.isfinite(tr.explained_variance())
 
 
-@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 64, 32), ("Acrobot-v1", 24, 64)])
+@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 64, 32), ("Acrobot-v1", 24, 64), ("MountainCar-v0", 32, 48)])
 def test_full_update_tensor_core_path_tracks_fp32_path(env_id, N, T):
     """Same seeds, one update: the tcgen05 (bf16) update must stay within bf16 tolerance of the fp32 update."""
     import deep_rl_b200 as drl

@@ -202,3 +202,35 @@ def test_vector_port_is_deterministic_and_learns_something():
         assert np.isfinite(out[-1]["loss"]) and np.abs(p.params - p0).max() > 1e-5
         runs.append(p.params.copy())
     assert np.array_equal(runs[0], runs[1])
+
+
+def test_mountaincar_oracle_matches_an_independent_restatement():
+    """MountainCar-v0 (gym 0.21 mountain_car.py, recalled): the C oracle against a straight Python float64 restatement of
+    the published update rule, over random actions incl. the inelastic left wall, the goal and the 200-step TimeLimit."""
+    import math
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        pos, vel = float(rng.uniform(-1.2, 0.6)), float(rng.uniform(-0.07, 0.07))
+        s = np.array([pos, vel])
+        for _ in range(300):
+            a = int(rng.integers(0, 3))
+            vel += (a - 1) * 0.001 + math.cos(3 * pos) * (-0.0025)
+            vel = min(max(vel, -0.07), 0.07)
+            pos += vel
+            pos = min(max(pos, -1.2), 0.6)
+            if pos == -1.2 and vel < 0:
+                vel = 0.0
+            done = bool(pos >= 0.5 and vel >= 0)
+            s, term = clib.mountaincar_step(s, a)
+            assert s[0] == pos and s[1] == vel and term == done
+            if done:
+                break
+    env = clib.OracleVecEnv("MountainCar-v0", 3, seed=4)
+    obs = env.reset()
+    assert obs.shape == (3, 2) and np.all((obs[:, 0] >= -0.6) & (obs[:, 0] <= -0.4)) and np.all(obs[:, 1] == 0)
+    lens = []
+    for t in range(450):
+        _, r, d, info = env.step(np.ones(3, dtype=np.int32))      # action 1 = no push: never reaches the goal
+        assert np.all(r == -1.0)
+        lens += [int(x) for x in info["final_length"][d.astype(bool)]]
+    assert lens and all(x == 200 for x in lens)                   # TimeLimit(200) of the MountainCar-v0 registration
