@@ -345,6 +345,35 @@ class PPOTrainer:
         # loss terms of the last minibatch (8 floats) followed by the pre-clip gradient norm: rows are contiguous
         return self._terms_and_norm[-9:]
 
+    # ------------------------------------------------------------------------------------------
+    def state_dict(self) -> Dict[str, object]:
+        """Everything needed to resume bit-identically: model + optimizer (ppo.py:86-90), counters, env state and the carried
+        reward / done slot of the one-slot-shifted storage (ppo.py:93-98).  Tensors are CPU copies (synchronises)."""
+        e = self.env
+        return {"model": {k: v.detach().cpu().clone() for k, v in self.agent.state_dict().items()},
+                "exp_avg": self.exp_avg.cpu().clone(), "exp_avg_sq": self.exp_avg_sq.cpu().clone(),
+                "adam_step": self.adam_step, "update_idx": self.update_idx, "global_step": self.global_step,
+                "env": {"state": e.state.cpu().clone(), "elapsed": e.elapsed.cpu().clone(), "ep_ret": e.ep_ret.cpu().clone(),
+                        "ep_len": e.ep_len.cpu().clone(), "step_count": e.step_count},
+                "carry": {"rewards0": self.rewards[0].cpu().clone(), "dones0": self.dones[0].cpu().clone()},
+                "config": {"env_id": self.cfg.env_id, "num_envs": self.cfg.num_envs, "num_steps": self.cfg.num_steps, "seed": self.cfg.seed}}
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        c = sd["config"]
+        if (c["env_id"], c["num_envs"], c["num_steps"]) != (self.cfg.env_id, self.cfg.num_envs, self.cfg.num_steps):
+            raise ValueError(f"checkpoint was taken with {c}, this trainer runs {self.cfg.env_id} x {self.cfg.num_envs} x {self.cfg.num_steps}")
+        self.agent.load_state_dict(sd["model"])
+        self.agent.sync()
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.adam_step, self.update_idx, self.global_step = int(sd["adam_step"]), int(sd["update_idx"]), int(sd["global_step"])
+        e, se = self.env, sd["env"]
+        e.state.copy_(se["state"]); e.elapsed.copy_(se["elapsed"]); e.ep_ret.copy_(se["ep_ret"]); e.ep_len.copy_(se["ep_len"])
+        e.step_count = int(se["step_count"])
+        self.rewards[0].copy_(sd["carry"]["rewards0"])
+        self.dones[0].copy_(sd["carry"]["dones0"])
+        self._perms_scheduled = False
+
     def explained_variance(self) -> float:
         """ppo.py:194-195 (computed over all T+1 slots like the reference)."""
         y, r = self.values.flatten(), self.returns.flatten()
