@@ -5,19 +5,20 @@
 // One persistent CTA per SM: 16 compute warps + 1 MMA-issuer warp + 1 loader warp.  A tile is 128 samples = the 128 TMEM lanes;
 // compute thread (warp w, lane l) owns sample row r = 32*(w&3)+l, net (w>>3) (0 = actor trunk, 1 = critic trunk) and
 // hidden units [32*((w>>2)&1), +32) of that net, i.e. four threads share a row.  Work per tile k:
-//   P0(k)  layer 1 on CUDA cores from the prefetched 32-byte record (K = 4/6 is degenerate for UMMA),
-//          h1 -> bf16 SW128 tile, [obs|1] -> NS16 tile
+//   MMA    l1(k):   z1 = [obs_hi|1|obs_lo] . [W1|b1|W1]^T (per net M128 N64 K16, no swizzle; the operand tile comes from the loader)
+//   P0(k)  tcgen05.ld z1, tanh, h1 -> bf16 SW128 tile
 //   MMA    fwd(k):  z2 = h1 . W2^T                      (per net M128 N64 K64, A/B K-major)
 //   P1(k)  tcgen05.ld z2, tanh, heads, clipped-surrogate / value / entropy loss and their closed-form output
 //          gradients, dz2 = (dout . W4) * (1 - h2^2); h2, dz2, dout -> bf16 tiles
-//   MMA    bwd(k):  dh1 = dz2 . W2                      (M128 N64 K64, B MN-major: the same W2 tile, transposed by descriptor)
+//   MMA    dh1(k):  dh1 = dz2 . W2                      (M128 N64 K64, B MN-major: the same W2 tile, transposed by descriptor)
+//   MMA    wg(k):   dW4 += h2^T . dout   db2 += dz2^T . [obs|1]          (M128 N16 K128)
 //                   dW2 += dz2^T . h1                   (M128 N128 K128, both operands MN-major: the activation tiles again)
-//                   db2 += dz2^T . [obs|1]   dW4 += h2^T . dout          (M128 N16 K128)
+//                   -- issued AFTER fwd(k+1): nobody waits for them until late in X(k+1)
 //   P2(k)  tcgen05.ld dh1, dz1 = dh1 * (1 - h1^2) -> bf16 tile
 //   MMA    w1(k):   [dW1|db1] += dz1^T . [obs|1]        (M128 N16 K128)
 // The loop is software-pipelined and warp-specialised so that no compute warp waits for a GEMM it has just
 // handed over, and no CTA-wide barrier sits in the loop:
-//   X(k): wait fwd(k), P1(k), hand bwd(k)   Y(k): P0(k+1), hand fwd(k+1)   Z(k): wait bwd(k), P2(k), hand w1(k)
+//   X(k): wait fwd(k), P1(k), hand dh1(k)   Y(k): wait l1(k+1), P0(k+1), hand fwd(k+1)   Z(k): wait dh1(k), P2(k), hand w1(k)
 // "hand" = fence.proxy.async + bar.arrive on a named barrier; the issuer warp bar.syncs on it, issues the
 // tcgen05.mma group and commits to an mbarrier the compute warps wait on.  h1 tiles are double-buffered, z2 and dh1
 // have separate TMEM columns.  The gather is decoupled from the compute warps: the loader warp reads the permuted
