@@ -323,13 +323,16 @@ def run_b200(args):
         except Exception:
             traffic = None
     tc = args.precision == "bf16"
-    roofline = {"kernel": ("ppo_grad_tc_kernel" if tc else "ppo_grad_kernel") + " (+grad_reduce_kernel)", "bound": "tensor", "achieved": achieved_tf,
+    roofline = {"kernel": ("ppo_grad_tc_kernel" if tc else "ppo_grad_kernel (+grad_reduce_kernel)"), "bound": "tensor", "achieved": achieved_tf,
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops_sustained"],
                 "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "flops_per_launch": flops_per_launch, "launch_ms": g["mean_ms"],
-                "note": ("tcgen05 path: the three HxH GEMMs and all weight-gradient reductions run on the tensor pipe (bf16 operands, "
-                         "fp32 TMEM accumulators); FLOPs counted are the algorithmic 3F per sample; launch_ms is the whole minibatch-step "
-                         "call (on one GPU the gradient kernel carries the fold + clip + Adam tail)" if tc else
+                "kernel_launch_includes": "gradient + fold of the per-SM partials + clip + Adam (one cooperative launch)" if tc else "gradient kernel only",
+                "limiter": ("shared-memory bandwidth: operand fetch of the 50 small tcgen05.mma per 128-sample tile + bf16 tile stores "
+                            "(DESIGN.md section 3, profiles/tools/mma_timing.cu)" if tc else "FP32 FMA issue"),
+                "note": ("tcgen05 path: every GEMM of the two 64-wide MLPs (layers 1-2 forward, dh1, all weight-gradient reductions) runs on the "
+                         "tensor pipe (bf16 operands, fp32 TMEM accumulators); FLOPs counted are the algorithmic 3F per sample; launch_ms is the "
+                         "whole minibatch-step call (the gradient kernel carries the fold + clip + Adam tail)" if tc else
                          "FP32 CUDA-core (FFMA) path; the tensor-pipe peak is the roof the tcgen05 path is held to"),
                 "hbm": {"achieved_gbs": GRAD_BYTES_PER_SAMPLE[args.env_id] * M / (g["mean_ms"] * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"]},
                 "end_to_end": {"hbm_frac": value * BYTES_PER_ENV_STEP[args.env_id] / world / 1e9 / peaks["hbm_gbs"],
