@@ -25,33 +25,60 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew,
     float v1 = val[(size_t)T * N + n];
     adv[(size_t)T * N + n] = 0.0f;
     ret[(size_t)T * N + n] = 0.0f + v1;
-#pragma unroll 4
-    for (int t = T - 1; t >= 0; --t) {
-        const size_t i0 = (size_t)t * N + n, i1 = i0 + N;
-        const float d = (float)done[i1];
-        const float r = rew[i1];
-        const float v0 = val[i0];
-        const float nd = 1.0f - d;
-        const float a = gamma * nd;
-        const float ll = lam * last;
-        const float b = v1 + ll;
-        const float c = a * b;
-        const float dd = r + c;
-        const float ad = dd - v0;
-        adv[i0] = ad;
-        ret[i0] = ad + v0;
-        if (rec != nullptr) {
-            float4* r4 = reinterpret_cast<float4*>(rec + i0 * RW);
-            const float4* o4 = reinterpret_cast<const float4*>(obs + i0 * OP);
-            r4[0] = o4[0];
-            if (RW == 16) {
-                r4[1] = o4[1];
-                r4[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // The recurrence is a chain of two dependent roundings per step; everything it reads is independent of it.  Each thread
+    // therefore fetches a block of GB steps (all loads in flight at once), then runs the chain over registers: with few envs
+    // per GPU the kernel is bound by load latency, not bandwidth.
+    constexpr int GB = 8;
+    for (int tb = T - 1; tb >= 0; tb -= GB) {
+        float r_[GB], v_[GB], lp_[GB];
+        uint8_t d_[GB], a_[GB];
+        float4 o_[GB][OP / 4];
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+            const int t = tb - j;
+            if (t >= 0) {
+                const size_t i0 = (size_t)t * N + n, i1 = i0 + N;
+                d_[j] = done[i1];
+                r_[j] = rew[i1];
+                v_[j] = val[i0];
+                if (rec != nullptr) {
+                    lp_[j] = logp[i0];
+                    a_[j] = act[i0];
+                    const float4* o4 = reinterpret_cast<const float4*>(obs + i0 * OP);
+#pragma unroll
+                    for (int q = 0; q < OP / 4; ++q) o_[j][q] = o4[q];
+                }
             }
-            r4[RW / 4 - 1] = make_float4(logp[i0], ad, v0, __int_as_float((int)act[i0]));
         }
-        last = ad;
-        v1 = v0;
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+            const int t = tb - j;
+            if (t >= 0) {
+                const size_t i0 = (size_t)t * N + n;
+                const float d = (float)d_[j];
+                const float v0 = v_[j];
+                const float nd = 1.0f - d;
+                const float a = gamma * nd;
+                const float ll = lam * last;
+                const float b = v1 + ll;
+                const float c = a * b;
+                const float dd = r_[j] + c;
+                const float ad = dd - v0;
+                adv[i0] = ad;
+                ret[i0] = ad + v0;
+                if (rec != nullptr) {
+                    float4* r4 = reinterpret_cast<float4*>(rec + i0 * RW);
+                    r4[0] = o_[j][0];
+                    if (RW == 16) {
+                        r4[1] = o_[j][OP / 4 - 1];
+                        r4[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    r4[RW / 4 - 1] = make_float4(lp_[j], ad, v0, __int_as_float((int)a_[j]));
+                }
+                last = ad;
+                v1 = v0;
+            }
+        }
     }
 }
 
