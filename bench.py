@@ -328,8 +328,9 @@ def run_b200(args):
                 "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "flops_per_launch": flops_per_launch, "launch_ms": g["mean_ms"],
                 "kernel_launch_includes": "gradient + fold of the per-SM partials + clip + Adam (one cooperative launch)" if tc else "gradient kernel only",
-                "limiter": ("shared-memory bandwidth: operand fetch of the 50 small tcgen05.mma per 128-sample tile + bf16 tile stores "
-                            "(DESIGN.md section 3, profiles/tools/mma_timing.cu)" if tc else "FP32 FMA issue"),
+                "limiter": ("no single pipe: per 128-sample tile a MUFU-bound tanh section, an issue-bound FMA section and three ~600-cycle "
+                            "tcgen05 round trips run back to back (one tile in flight per SM); the small GEMM instructions are bound by "
+                            "operand fetch from shared memory, not math (DESIGN.md section 3, profiles/tools/mma_timing.cu)" if tc else "FP32 FMA issue"),
                 "note": ("tcgen05 path: every GEMM of the two 64-wide MLPs (layers 1-2 forward, dh1, all weight-gradient reductions) runs on the "
                          "tensor pipe (bf16 operands, fp32 TMEM accumulators); FLOPs counted are the algorithmic 3F per sample; launch_ms is the "
                          "whole minibatch-step call (the gradient kernel carries the fold + clip + Adam tail)" if tc else
