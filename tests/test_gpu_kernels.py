@@ -163,7 +163,7 @@ def test_single_env_gym_api_episode_info():
 # ------------------------------------------------------------------------------------------------
 # model forward
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("O,A", [(4, 2), (6, 3)])
+@pytest.mark.parametrize("O,A", [(4, 2), (6, 3), (2, 3)])
 @pytest.mark.parametrize("n", [1, 7, 8, 1000, 65537])
 def test_policy_forward_vs_torch(O, A, n):
     L = _lib()
@@ -320,7 +320,7 @@ def test_minibatch_grad_vs_reference_golden(golden):
         params = g["mb_params_after"][i]
 
 
-@pytest.mark.parametrize("O,A,B,M", [(4, 2, 4096, 1024), (6, 3, 3000, 750), (4, 2, 100_000, 25_000), (4, 2, 70, 70)])
+@pytest.mark.parametrize("O,A,B,M", [(4, 2, 4096, 1024), (6, 3, 3000, 750), (4, 2, 100_000, 25_000), (4, 2, 70, 70), (2, 3, 2000, 500)])
 def test_minibatch_grad_vs_torch_oracle(O, A, B, M):
     rng = np.random.default_rng(B)
     torch.manual_seed(B)
@@ -393,7 +393,7 @@ def test_tc_minibatch_grad_vs_reference_golden(golden):
         params = g["mb_params_after"][i]
 
 
-@pytest.mark.parametrize("O,A,B,M", [(4, 2, 4096, 1024), (6, 3, 3000, 750), (4, 2, 100_000, 25_000), (4, 2, 70, 70), (4, 2, 129, 129)])
+@pytest.mark.parametrize("O,A,B,M", [(4, 2, 4096, 1024), (6, 3, 3000, 750), (4, 2, 100_000, 25_000), (4, 2, 70, 70), (4, 2, 129, 129), (2, 3, 2000, 500)])
 def test_tc_minibatch_grad_vs_torch_oracle(O, A, B, M):
     rng = np.random.default_rng(B)
     RW = 8 if O <= 4 else 16
