@@ -2,6 +2,7 @@
 
     python examples/learning_curve.py            # reference shape (1 env x 128 steps, 20k timesteps), seeds 1..5
     python examples/learning_curve.py 4096 60    # 4096 envs, 60 updates
+    python examples/learning_curve.py 4096 60 Acrobot-v1
 """
 import os
 import sys
@@ -27,8 +28,8 @@ def reference_shape():
             print(f"b200 {prec} seed {seed}: {len(rets)} episodes, first-20 mean {np.mean(rets[:20]):.1f}, last-20 mean {np.mean(rets[-20:]):.1f}")
 
 
-def many_envs(n, updates):
-    cfg = drl.PPOConfig(num_envs=n, total_timesteps=n * 128 * updates, seed=1)
+def many_envs(n, updates, env_id="CartPole-v1"):
+    cfg = drl.PPOConfig(env_id=env_id, num_envs=n, total_timesteps=n * 128 * updates, seed=1)
     tr = drl.PPOTrainer(cfg)
     for u in range(updates):
         tr.update()
@@ -40,6 +41,6 @@ def many_envs(n, updates):
 
 if __name__ == "__main__":
     if len(sys.argv) > 2:
-        many_envs(int(sys.argv[1]), int(sys.argv[2]))
+        many_envs(int(sys.argv[1]), int(sys.argv[2]), *(sys.argv[3:4]))
     else:
         reference_shape()
