@@ -686,7 +686,8 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(tl.peer[tl.rank] + cl.flags[gen] + 4 * tid);
             const long long t0 = clock64();
             while (*f < tl.seq) {
-                if (clock64() - t0 > 8000000000ll) { if (tl.error_flag) *tl.error_flag = 1; break; }   // ~4 s: a peer is gone
+                if (clock64() - t0 > 40000000000ll) { if (tl.error_flag) *tl.error_flag = 1; break; }   // ~20 s: a peer is gone (start-up skew
+                                                                                                   // between ranks can reach seconds)
             }
             __threadfence_system();
         }
