@@ -20,7 +20,6 @@ from __future__ import annotations
 import argparse
 import contextlib
 import ctypes as C
-import math
 from dataclasses import dataclass
 from typing import Dict, Optional
 

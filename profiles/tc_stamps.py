@@ -1,5 +1,4 @@
 """Cycle-stamp timeline of ppo_grad_tc_kernel (CTA 0), DRL_TC_DEBUG=1.  Usage: DRL_TC_DEBUG=1 python profiles/tc_stamps.py"""
-import ctypes as C
 import os
 import sys
 
@@ -9,7 +8,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["DRL_TC_DEBUG"] = "1"
 import deep_rl_b200 as drl  # noqa: E402
-from deep_rl_b200 import _lib as L  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 cfg = drl.PPOConfig(num_envs=N, num_steps=128, total_timesteps=N * 128 * 8)
