@@ -103,6 +103,15 @@ def test_tensor_core_rollout_vs_oracle(env_id, N, T):
 
 
 @pytest.mark.parametrize("rows", [32, 64, 128])
+def test_tensor_core_rollout_every_row_variant(rows, monkeypatch):
+    """The launcher picks 32 / 64 / 128 envs per CTA (each env on 4 / 2 / 1 GEMM rows) from the env count; force each
+    variant on the same small problem."""
+    monkeypatch.setenv("DRL_ROLLOUT_ROWS", str(rows))
+    _check_rollout("CartPole-v1", 200, 24, seed=4, tc=True)
+    _check_rollout("Acrobot-v1", 70, 16, seed=4, tc=True)
+
+
+@pytest.mark.parametrize("rows", [32, 64, 128])
 def test_tensor_core_rollout_rows_per_cta(rows):
     """Few envs spread over more CTAs (32 / 64 rows of the 128-row tile used): same results as the oracle."""
     os.environ["DRL_ROLLOUT_ROWS"] = str(rows)
