@@ -234,3 +234,41 @@ def test_mountaincar_oracle_matches_an_independent_restatement():
         assert np.all(r == -1.0)
         lens += [int(x) for x in info["final_length"][d.astype(bool)]]
     assert lens and all(x == 200 for x in lens)                   # TimeLimit(200) of the MountainCar-v0 registration
+
+
+def test_permutation_inverse_property():
+    """hypothesis: for arbitrary sizes, seeds, epochs and ranks the keyed Feistel permutation is a bijection and
+    perm_position is its inverse (the statistics kernel relies on it to find a sample's minibatch without a gather)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(B=st.integers(1, 3000), seed=st.integers(0, 2**63 - 1), epoch=st.integers(0, 2**31 - 1), rank=st.integers(0, 7))
+    def check(B, seed, epoch, rank):
+        p = clib.permutation(B, seed=seed, epoch_ctr=epoch, rank=rank)
+        assert np.array_equal(np.sort(p), np.arange(B, dtype=np.uint32))
+        L = clib.lib()
+        for i in (0, B // 3, B - 1):
+            x = L.drl_or_perm_index(i, B, seed, epoch, rank)
+            assert x == p[i] and L.drl_or_perm_position(int(x), B, seed, epoch, rank) == i
+
+    check()
+
+
+def test_gae_matches_a_straight_numpy_restatement():
+    """The C oracle's GAE (pinned bit-exactly against the reference's own buffers above) against an independent float64
+    evaluation of ppo.py:144-151 on random inputs: agreement to fp32 rounding for arbitrary shapes."""
+    rng = np.random.default_rng(5)
+    for T, N in [(1, 1), (7, 3), (128, 17)]:
+        rew = rng.uniform(0, 1, size=(T + 1, N)).astype(np.float32)
+        done = (rng.uniform(size=(T + 1, N)) < 0.1).astype(np.float32)
+        val = rng.normal(size=(T + 1, N)).astype(np.float32)
+        adv, ret = clib.gae(rew, done, val, 0.99, 0.95)
+        want = np.zeros((T + 1, N))
+        last = np.zeros(N)
+        for t in reversed(range(T)):
+            nonterminal = 1.0 - done[t + 1].astype(np.float64)
+            delta = rew[t + 1] + 0.99 * val[t + 1].astype(np.float64) * nonterminal - val[t]
+            last = delta + 0.99 * 0.95 * nonterminal * last
+            want[t] = last
+        np.testing.assert_allclose(adv[:T], want[:T], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(ret[:T], want[:T] + val[:T], rtol=2e-5, atol=2e-5)
