@@ -95,7 +95,10 @@ int64_t drl_param_count(const drl_net_t* net);
 int64_t drl_packed_count(const drl_net_t* net);
 /* sample-record width in floats (8 for O<=4, 16 otherwise) */
 int drl_record_width(const drl_net_t* net);
-/* bytes of zero-initialised scratch the update entry points need */
+/* bytes of zero-initialised scratch the update entry points need.  One workspace serves one trainer: calls on the SAME stream
+ * may share it freely; the statistics calls (drl_adv_stats, drl_adv_stats_perm) use regions disjoint from those of the
+ * minibatch calls, so they may also run on a second stream while a minibatch step is in flight (but not two statistics
+ * calls, or two minibatch calls, concurrently). */
 size_t drl_workspace_bytes(const drl_net_t* net);
 
 /* ---- environment (ppo.py:17,21,79,101,127-129) ---- */
