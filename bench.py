@@ -166,12 +166,13 @@ def _single_env_processes(updates: int, warm: int):
     return sum(r[0] for r in res) / max(r[1] for r in res), procs_n
 
 
-def _workload_name(world: int, envs: int, T: int, env_id: str) -> str:
-    if world == 1 and envs == 4096 and T == 128 and env_id == "CartPole-v1":
+def _workload_name(world: int, envs: int, T: int, env_id: str, hidden: int = 64) -> str:
+    if world == 1 and envs == 4096 and T == 128 and env_id == "CartPole-v1" and hidden == 64:
         return "C2: PPO CartPole-v1, 4096 envs x 128 steps, 64-wide MLP, 1xB200"
-    if envs == 65_536 and T == 128 and env_id == "CartPole-v1":
-        return f"C3: PPO CartPole-v1, 65,536 envs/GPU x 128 steps env-sharded across {world} B200, NCCL gradient all-reduce"
-    return f"custom: {env_id}, {envs} envs/GPU x {T} steps"
+    if envs == 65_536 and T == 128 and env_id == "CartPole-v1" and hidden == 64:
+        return (f"C3: PPO CartPole-v1, 65,536 envs/GPU x 128 steps env-sharded across {world} B200, one gradient all-reduce per minibatch "
+                f"(in-kernel over NVLink peer memory; NCCL with --grad-allreduce nccl)")
+    return f"custom: {env_id}, {envs} envs/GPU x {T} steps, {hidden}-wide MLP"
 
 
 def _vector_port_sample(env_id: str, envs: int, T: int, updates: int, warm: int, budget_s: float):
@@ -213,7 +214,7 @@ def run_reference(args):
     value, per_update, used, threads = _vector_port_sample(args.env_id, envs, T, args.steps, args.warmup, budget_s=150.0)
     single, procs_n = _single_env_processes(min(args.steps, 5), 1)
     wall = time.perf_counter() - t_all
-    B = envs * T
+    B = used * T
     sample = (f"{args.steps} updates of the N-env CPU port (oracle/ppo_vector_port.py: batched PyTorch CPU ops + C env/sampler/GAE) with "
               f"{used} envs x {T} steps on {threads} host threads after {max(1, args.warmup)} warm-up update(s), {per_update:.2f} s per update"
               + ("" if used == envs else f"; bounded sample: {used} of the {envs} envs per GPU, same per-env-step work")
@@ -222,8 +223,10 @@ def run_reference(args):
         "impl": "reference", "metric": "PPO env-steps/sec (rollout+update) CartPole-v1", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_update,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": _workload_name(world, envs, T, args.env_id), "precision": "fp32 (PyTorch CPU)", "env_id": args.env_id,
-                   "envs_per_gpu": envs, "num_steps": T, "hidden": 64, "minibatch_size": (B + 3) // 4, "update_epochs": 4,
+        "config": {"workload": _workload_name(world, envs, T, args.env_id) + ("" if used == envs else
+                                                                              f" -- CPU arm bounded to {used} of the {envs} envs per GPU"),
+                   "precision": "fp32 (PyTorch CPU)", "env_id": args.env_id,
+                   "envs_per_gpu": used, "envs_per_gpu_of_the_gpu_arm": envs, "num_steps": T, "hidden": 64, "minibatch_size": (B + 3) // 4, "update_epochs": 4,
                    "optimizer_steps_per_update": 16, "parallelism": f"host CPU, {threads} threads (no GPU)"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "single_env_reference_shape": {"value": single, "unit": "env-steps/s", "processes": procs_n},
@@ -236,6 +239,184 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
+GAE_BYTES = {"CartPole-v1": 17 + 21 + 32, "Acrobot-v1": 17 + 29 + 64, "MountainCar-v0": 17 + 21 + 32}   # planes + record packing
+ROLLOUT_BYTES = {"CartPole-v1": 30, "Acrobot-v1": 38, "MountainCar-v0": 30}
+ENV_STEP_BYTES = {"CartPole-v1": 62 + 32, "Acrobot-v1": 70 + 32, "MountainCar-v0": 62 + 32}             # SURVEY 8d + fp64 state r/w
+
+
+def _timed_updates(tr, nu, steps, flush, dist, dev):
+    """`steps` updates, each bracketed by CUDA events on the launching stream with the L2 flushed before it (outside the
+    events).  Returns (sum of event ms -- max over ranks, per-phase ms, kernel launches)."""
+    import torch
+    tr.timing = True
+    tr.phase_events.clear()
+    launches0 = tr.kernel_launches
+    evs = []
+    dist.barrier()
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tr.update(nu)
+        e1.record()
+        evs.append((e0, e1))
+    return evs, launches0
+
+
+def _finish_timed(tr, evs, launches0, dist, dev):
+    import torch
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = tr.kernel_launches - launches0
+    phases = tr.phase_ms()
+    tr.timing = False
+    local_ms = sum(a.elapsed_time(b) for a, b in evs)
+    return dist.all_reduce_max(local_ms, dev), local_ms, phases, launches
+
+
+def _grad_roofline(env_id, hidden, M, phases, total_ms, value, world, tc, peaks, traffic=None):
+    F = flops_fwd(env_id, hidden)
+    g = phases.get("minibatch_grad", {"mean_ms": float("nan"), "total_ms": 0.0})
+    flops_per_launch = 3 * F * M
+    achieved_tf = flops_per_launch / (g["mean_ms"] * 1e-3) / 1e12
+    return {"kernel": ("ppo_grad_tc_kernel" if tc else "ppo_grad_kernel (+grad_reduce_kernel)") if hidden == 64 else "ppo_grad256 kernels",
+            "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": traffic,
+            "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+            "flops_per_launch": flops_per_launch, "launch_ms": g["mean_ms"],
+            "hbm": {"achieved_gbs": GRAD_BYTES_PER_SAMPLE[env_id] * M / (g["mean_ms"] * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"]},
+            "end_to_end": {"hbm_frac": value * BYTES_PER_ENV_STEP[env_id] / world / 1e9 / peaks["hbm_gbs"],
+                           "tensor_frac": value * 13 * F / world / 1e12 / peaks["bf16_tflops_sustained"]},
+            "share_of_step": g["total_ms"] / max(1e-9, total_ms)}
+
+
+def flops_fwd(env_id, hidden):
+    O, A = {"CartPole-v1": (4, 2), "Acrobot-v1": (6, 3), "MountainCar-v0": (2, 3)}[env_id]
+    return 2 * (O * hidden + hidden * hidden + hidden * A) + 2 * (O * hidden + hidden * hidden + hidden)      # SURVEY.md 8d
+
+
+def _hbm_rooflines(env_id, envs, T, E, phases, peaks):
+    """HBM fractions of the bandwidth-bound kernels from the CUDA events recorded around each call inside the timed region
+    (algorithmic bytes per sample: SURVEY.md 8d / DESIGN.md section 3)."""
+    B = envs * T
+    out = []
+    for name, kernel, nbytes, per in (("gae", "gae_kernel", GAE_BYTES[env_id] * B, "update"),
+                                      ("rollout", "rollout kernel", ROLLOUT_BYTES[env_id] * B, "update"),
+                                      ("permutation", "permutation_kernel", 4 * B, "epoch"),
+                                      ("adv_stats", "adv_stats_perm_kernel", 4 * B, "epoch")):
+        ph = phases.get(name)
+        if not ph or not ph["mean_ms"]:
+            continue
+        gbs = nbytes / (ph["mean_ms"] * 1e-3) / 1e9
+        out.append({"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": nbytes, "launch_ms": ph["mean_ms"], "per": per})
+    return out
+
+
+def _env_step_roofline(env_id, dev, peaks, n_envs=1 << 20, steps=20):
+    """One-off timing of the stand-alone env_step_kernel (drl_env_step: state in HBM) on n_envs environments."""
+    import torch
+    import deep_rl_b200 as drl
+    env = drl.make(env_id, num_envs=n_envs, seed=3, device=dev)
+    env.reset()
+    act = torch.zeros(n_envs, dtype=torch.int32, device=dev)
+    import ctypes as C
+    from deep_rl_b200 import _lib
+    call = lambda k: _lib.check(env.L.drl_env_step(C.byref(env.struct), k, act.data_ptr(), env._obs.data_ptr(), env._rew.data_ptr(),
+                                                   env._done.data_ptr(), C.byref(env.log.struct), _lib.stream_ptr()))
+    for k in range(3):
+        call(k)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        call(3 + k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    nbytes = ENV_STEP_BYTES[env_id] * n_envs
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "env_step_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+            "bytes_per_launch": nbytes, "launch_ms": ms, "per": "env step", "envs": n_envs,
+            "note": "stand-alone drl_env_step (fp64 state read + written in HBM every step; 1 Mi envs, back-to-back launches, "
+                    "working set below the L2 size, so this is an upper bound on the HBM-resident rate); the training loop uses "
+                    "the fused rollout, whose state lives in registers"}
+
+
+def _run_config(name, env_id, envs, T, hidden, steps, warm, rank, world, dev, flush, dist, peaks, precision="auto", grad_allreduce="peer"):
+    """One extra workload (BASELINE.json configs C4 / C5 / C3-on-one-GPU) timed like the headline one."""
+    import torch
+    from deep_rl_b200 import PPOConfig, PPOTrainer
+    total_updates = warm + steps + 4
+    cfg = PPOConfig(env_id=env_id, num_envs=envs, num_steps=T, hidden=hidden, total_timesteps=envs * T * world * total_updates, seed=1,
+                    update_precision=precision, grad_allreduce=grad_allreduce)
+    tr = PPOTrainer(cfg, rank=rank, world=world, device=dev)
+    nu = cfg.num_updates(world)
+    for _ in range(warm):
+        tr.update(nu)
+    torch.cuda.synchronize()
+    evs, l0 = _timed_updates(tr, nu, steps, flush, dist, dev)
+    dev_ms, local_ms, phases, launches = _finish_timed(tr, evs, l0, dist, dev)
+    m = tr.metrics(with_episode_log=False)
+    value = envs * T * world * steps / (dev_ms * 1e-3)
+    tc = tr.update_precision == "bf16"
+    rec = {"name": name, "workload": f"{env_id}, {envs} envs/GPU x {T} steps, {hidden}-wide MLP, {world} GPU(s)", "value": value,
+           "unit": "env-steps/s", "ms_per_step": dev_ms / steps, "steps": steps, "warmup": warm, "n_gpus": world,
+           "dtype": "bf16" if tc else "f32", "episodes_dropped": m["episodes_dropped"],
+           "roofline": _grad_roofline(env_id, hidden, cfg.minibatch_size, phases, local_ms, value, world, tc, peaks),
+           "rooflines": _hbm_rooflines(env_id, envs, T, cfg.update_epochs, phases, peaks),
+           "phases_ms_per_update": {k: v["total_ms"] / steps for k, v in phases.items()}, "gpu_launches": launches}
+    if tr.peer is not None:
+        tr.peer.close()
+    del tr
+    torch.cuda.empty_cache()
+    return rec
+
+
+def _params_checksum(tr):
+    """64-bit checksum of the parameters and the second Adam moment (exact integer sums of the raw bit patterns)."""
+    import torch
+    a = tr.agent.flat_params.view(torch.int32).to(torch.int64)
+    b = tr.exp_avg_sq.view(torch.int32).to(torch.int64)
+    w = torch.arange(1, a.numel() + 1, device=a.device, dtype=torch.int64)
+    return int(((a * w).sum() + 31 * (b * w).sum()).item())
+
+
+def _multi_gpu_checks(tr, nu, dev, world):
+    """Driver-visible multi-GPU correctness (GPUTEST runs on one GPU): (1) every rank holds bit-identical parameters and Adam
+    moments after the timed updates; (2) two more updates from the same state through the in-kernel peer all-reduce and
+    through NCCL (drl_ppo_minibatch_grad -> torch.distributed.all_reduce -> drl_clip_adam) agree to fp32 rounding."""
+    import torch
+    import torch.distributed as td
+    out = {}
+    torch.cuda.synchronize()
+    mine = torch.tensor([_params_checksum(tr)], dtype=torch.int64, device=dev)
+    allc = [torch.zeros_like(mine) for _ in range(world)]
+    td.all_gather(allc, mine)
+    out["ranks_bit_identical"] = bool(all(int(c.item()) == int(allc[0].item()) for c in allc))
+    if tr.peer is not None:
+        sd = tr.state_dict()
+        tr.update(nu); tr.update(nu)
+        torch.cuda.synchronize()
+        p_peer = tr.agent.flat_params.clone()
+        tr.load_state_dict(sd)
+        peer, tr.peer = tr.peer, None                # same trainer, NCCL exchange between the kernels
+        tr.update(nu); tr.update(nu)
+        torch.cuda.synchronize()
+        p_nccl = tr.agent.flat_params.clone()
+        tr.peer = peer
+        tr.load_state_dict(sd)
+        diff = torch.tensor([float((p_peer - p_nccl).abs().max().item())], dtype=torch.float64, device=dev)
+        td.all_reduce(diff, op=td.ReduceOp.MAX)
+        out["peer_vs_nccl_max_abs"] = float(diff.item())
+        out["peer_vs_nccl_param_scale"] = float(p_nccl.abs().max().item())
+        c2 = torch.tensor([_params_checksum(tr)], dtype=torch.int64, device=dev)
+        alld = [torch.zeros_like(c2) for _ in range(world)]
+        td.all_gather(alld, c2)
+        out["ranks_bit_identical"] = out["ranks_bit_identical"] and bool(all(int(c.item()) == int(alld[0].item()) for c in alld))
+    return out
+
+
 def run_b200(args):
     import torch
     from deep_rl_b200 import PPOConfig, PPOTrainer, dist
@@ -246,18 +427,32 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    peaks = load_peaks()
 
     envs = args.envs_per_gpu if args.envs_per_gpu else (4096 if world == 1 else 65_536)
     T = args.num_steps
-    workload = _workload_name(world, envs, T, args.env_id)
-    total_updates = args.warmup + 2 * args.steps + 8
-    cfg = PPOConfig(env_id=args.env_id, num_envs=envs, num_steps=T, total_timesteps=envs * T * world * total_updates, seed=1,
+    hidden = args.hidden
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    headline = envs in (4096, 65_536) and T == 128 and args.env_id == "CartPole-v1" and hidden == 64
+
+    # ---- N > 1: the per-GPU workload on ONE GPU first (every rank runs its own world-1 trainer), so that the scaling
+    # efficiency can be read off like for like in the same run ----
+    single = None
+    if world > 1 and not args.no_scaling_reference:
+        single = _run_config("per-GPU workload on one GPU", args.env_id, envs, T, hidden, args.steps, max(3, args.warmup), 0, 1, dev, flush,
+                             _SoloDist(), peaks, precision=args.precision)
+        single_ms = dist.all_reduce_max(single["ms_per_step"], dev)
+        single["ms_per_step_max_over_ranks"] = single_ms
+
+    workload = _workload_name(world, envs, T, args.env_id, hidden)
+    total_updates = args.warmup + 2 * args.steps + 16
+    cfg = PPOConfig(env_id=args.env_id, num_envs=envs, num_steps=T, hidden=hidden, total_timesteps=envs * T * world * total_updates, seed=1,
                     update_precision=args.precision, grad_allreduce=args.grad_allreduce)
     tr = PPOTrainer(cfg, rank=rank, world=world, device=dev)
     nu = cfg.num_updates(world)
     n_mb = tr.n_mb
     tr_peer = tr.peer is not None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    tc = tr.update_precision == "bf16"
 
     for _ in range(max(3, args.warmup)):
         tr.update(nu)
@@ -266,27 +461,9 @@ def run_b200(args):
 
     # ---- device-resident timing: per-update CUDA events, L2 flushed between updates ----
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
-    tr.timing = True
-    tr.phase_events.clear()
-    launches0 = tr.kernel_launches
-    evs = []
-    dist.barrier()
-    torch.cuda.synchronize()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        tr.update(nu)
-        e1.record()
-        evs.append((e0, e1))
+    evs, l0 = _timed_updates(tr, nu, args.steps, flush, dist, dev)
     clocks = sampler.stop() if sampler else None      # last sample while the queued updates are still running
-    torch.cuda.synchronize()
-    dist.barrier()
-    launches = tr.kernel_launches - launches0
-    phases = tr.phase_ms()
-    tr.timing = False
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    dev_ms = dist.all_reduce_max(dev_ms, dev)
+    dev_ms, local_ms, phases, launches = _finish_timed(tr, evs, l0, dist, dev)
     steps_per_update = envs * T * world
     value = steps_per_update * args.steps / (dev_ms * 1e-3)
 
@@ -294,77 +471,75 @@ def run_b200(args):
     tr.metrics()
     dist.barrier()
     torch.cuda.synchronize()
-    d2h = 0
+    d2h, dropped = 0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         tr.update(nu)
         # D2H every update, like the reference's prints: loss terms + grad norm (36 B), episode count + sums (24 B) and the
-        # (step, env, return, length) record of every finished episode (20 B each, up to the log capacity)
+        # (step, env, return, length) record of every finished episode (20 B each)
         m = tr.metrics(with_episode_log="arrays")
         d2h += 36 + tr.env.log.last_d2h_bytes
+        dropped += m["episodes_dropped"]
         _ = (m["mean_return"], m["loss"], len(m["episode_log"]["ret"]))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_s = dist.all_reduce_max(e2e_s, dev)
     e2e_value = steps_per_update * args.steps / e2e_s
+    assert dropped == 0, f"{dropped} finished episodes did not fit the episode log: e2e would not read what the reference prints"
 
-    # ---- roofline of the dominant kernel (ppo_grad + its fixed-order reduce) ----
-    peaks = load_peaks()
-    F = F_FWD[(args.env_id, 64)]
+    # ---- roofline of the dominant kernel + the bandwidth-bound kernels ----
     M = cfg.minibatch_size
-    g = phases.get("minibatch_grad", {"mean_ms": float("nan"), "total_ms": 0.0})
-    flops_per_launch = 3 * F * M
-    achieved_tf = flops_per_launch / (g["mean_ms"] * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"{'ppo_grad_tc_kernel' if args.precision == 'bf16' else 'ppo_grad_kernel'}@{M}")
+            traffic = json.load(open(tpath)).get(f"{'ppo_grad_tc_kernel' if tc else 'ppo_grad_kernel'}@{M}")
         except Exception:
             traffic = None
-    tc = args.precision == "bf16"
-    roofline = {"kernel": ("ppo_grad_tc_kernel" if tc else "ppo_grad_kernel (+grad_reduce_kernel)"), "bound": "tensor", "achieved": achieved_tf,
-                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops_sustained"],
-                "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "flops_per_launch": flops_per_launch, "launch_ms": g["mean_ms"],
-                "kernel_launch_includes": "gradient + fold of the per-SM partials + clip + Adam (one cooperative launch)" if tc else "gradient kernel only",
-                "limiter": ("no single pipe: per 128-sample tile a MUFU-bound tanh section, an issue-bound FMA section and three ~600-cycle "
-                            "tcgen05 round trips run back to back (one tile in flight per SM); the small GEMM instructions are bound by "
-                            "operand fetch from shared memory, not math (DESIGN.md section 3, profiles/tools/mma_timing.cu)" if tc else "FP32 FMA issue"),
-                "note": ("tcgen05 path: every GEMM of the two 64-wide MLPs (layers 1-2 forward, dh1, all weight-gradient reductions) runs on the "
-                         "tensor pipe (bf16 operands, fp32 TMEM accumulators); FLOPs counted are the algorithmic 3F per sample; launch_ms is the "
-                         "whole minibatch-step call (the gradient kernel carries the fold + clip + Adam tail)" if tc else
-                         "FP32 CUDA-core (FFMA) path; the tensor-pipe peak is the roof the tcgen05 path is held to"),
-                "hbm": {"achieved_gbs": GRAD_BYTES_PER_SAMPLE[args.env_id] * M / (g["mean_ms"] * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"]},
-                "end_to_end": {"hbm_frac": value * BYTES_PER_ENV_STEP[args.env_id] / world / 1e9 / peaks["hbm_gbs"],
-                               "tensor_frac": value * 13 * F / world / 1e12 / peaks["bf16_tflops_sustained"]},
-                "share_of_step": g["total_ms"] / max(1e-9, sum(a.elapsed_time(b) for a, b in evs))}
+    roofline = _grad_roofline(args.env_id, hidden, M, phases, local_ms, value, world, tc, peaks, traffic)
+    roofline.update({
+        "kernel_launch_includes": "gradient + fold of the per-SM partials + clip + Adam (one cooperative launch)" if tc else "gradient kernel only",
+        "limiter": ("no single pipe: per 128-sample tile a MUFU-bound tanh section, an issue-bound FMA section and three ~600-cycle "
+                    "tcgen05 round trips run back to back (one tile in flight per SM); the small GEMM instructions are bound by "
+                    "operand fetch from shared memory, not math (DESIGN.md section 3, profiles/tools/mma_timing.cu)" if tc else "FP32 FMA issue"),
+        "note": ("tcgen05 path: every GEMM of the two MLPs (layers 1-2 forward, dh1, all weight-gradient reductions) runs on the "
+                 "tensor pipe (bf16 operands, fp32 TMEM accumulators); FLOPs counted are the algorithmic 3F per sample; launch_ms is the "
+                 "whole minibatch-step call (the gradient kernel carries the fold + clip + Adam tail)" if tc else
+                 "FP32 CUDA-core (FFMA) path; the tensor-pipe peak is the roof the tcgen05 path is held to")})
+    rooflines = _hbm_rooflines(args.env_id, envs, T, cfg.update_epochs, phases, peaks)
 
-    # ---- N = 1 only: the multi-GPU workload (C3) on this one GPU, so that scaling can be read off like-for-like ----
-    scaling_ref = None
-    if world == 1 and envs == 4096 and args.env_id == "CartPole-v1" and not args.no_scaling_reference:
-        del tr
-        torch.cuda.empty_cache()
-        cfg3 = PPOConfig(env_id=args.env_id, num_envs=65_536, num_steps=T, total_timesteps=65_536 * T * 64, seed=1,
-                         update_precision=args.precision)
-        tr3 = PPOTrainer(cfg3, rank=0, world=1, device=dev)
-        for _ in range(3):
-            tr3.update(64)
-        torch.cuda.synchronize()
-        ev3 = []
-        for _ in range(5):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); tr3.update(64); e1.record()
-            ev3.append((e0, e1))
-        torch.cuda.synchronize()
-        ms3 = sum(a.elapsed_time(b) for a, b in ev3) / 5
-        scaling_ref = {"workload": "C3 (65,536 envs x 128 steps) on this one GPU: the per-GPU work of the N>1 runs",
-                       "value": 65_536 * T / (ms3 * 1e-3), "unit": "env-steps/s", "ms_per_step": ms3, "steps": 5}
-        del tr3
-
-    if world > 1 and tr_peer:
+    multi = _multi_gpu_checks(tr, nu, dev, world) if world > 1 else None
+    if tr_peer:
         tr.peer.close()
+    del tr
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations, timed the same way (the driver only runs the default command line) ----
+    extra, fp32_path, scaling_ref = [], None, None
+    if headline and not args.no_extra_configs:
+        xs = max(3, min(args.steps, 10))
+        if world == 1:
+            rooflines.append(_env_step_roofline(args.env_id, dev, peaks))
+            scaling_ref = _run_config("C3 on one GPU (the per-GPU work of the N>1 runs)", "CartPole-v1", 65_536, 128, 64, args.steps, 3,
+                                      0, 1, dev, flush, dist, peaks)
+            extra.append(_run_config("C4: PPO Acrobot-v1, 16,384 envs x 256 steps, 1xB200", "Acrobot-v1", 16_384, 256, 64, xs, 3, 0, 1, dev,
+                                     flush, dist, peaks))
+            f32 = _run_config("strict fp32 path (CUDA cores) on the headline workload", args.env_id, envs, T, 64, 3, 3, 0, 1, dev, flush, dist,
+                              peaks, precision="fp32")
+            fp32_path = {"value": f32["value"], "unit": "env-steps/s", "ms_per_step": f32["ms_per_step"], "workload": workload}
+            if args.hidden256:
+                extra.append(_run_config("C5: synthetic stress, 1M envs x 256 steps, 256-wide MLP, 1xB200", "CartPole-v1", 1 << 20, 256, 256,
+                                         2, 1, 0, 1, dev, flush, dist, peaks))
+        else:
+            per = 16_384 // world
+            extra.append(_run_config(f"C4 strong scaling: Acrobot-v1, 16,384 envs total ({per}/GPU) x 256 steps", "Acrobot-v1", per, 256, 64, xs, 3,
+                                     rank, world, dev, flush, dist, peaks))
+            extra.append(_run_config("C4 weak scaling: Acrobot-v1, 16,384 envs/GPU x 256 steps", "Acrobot-v1", 16_384, 256, 64, xs, 3,
+                                     rank, world, dev, flush, dist, peaks))
+            if args.hidden256:
+                extra.append(_run_config(f"C5: synthetic stress, 1M envs total ({(1 << 20) // world}/GPU) x 256 steps, 256-wide MLP",
+                                         "CartPole-v1", (1 << 20) // world, 256, 256, 3, 1, rank, world, dev, flush, dist, peaks))
+
     if rank != 0:
         dist.shutdown()
         return
@@ -389,21 +564,40 @@ def run_b200(args):
         "metric": "PPO env-steps/sec (rollout+update) CartPole-v1", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tc else "f32", "data": "synthetic",
-        "config": {"workload": workload, "precision": ("update GEMMs bf16 x bf16 -> fp32 on tcgen05; rollout, env, GAE, loss, Adam fp32/fp64" if tc else "fp32"), "env_id": args.env_id, "envs_per_gpu": envs, "num_steps": T, "hidden": 64,
+        "config": {"workload": workload, "precision": ("rollout + update GEMMs bf16 x bf16 -> fp32 on tcgen05; env fp64; GAE, loss, Adam fp32" if tc else "fp32"),
+                   "env_id": args.env_id, "envs_per_gpu": envs, "num_steps": T, "hidden": hidden,
                    "minibatch_size": M, "update_epochs": cfg.update_epochs, "optimizer_steps_per_update": cfg.update_epochs * n_mb,
                    "parallelism": f"env-sharded x{world}" + ("" if world == 1 else (", gradient all-reduce inside the gradient kernel over NVLink peer memory"
                                                                                   if tr_peer else ", NCCL gradient all-reduce per minibatch")), "l2": "flushed between updates (256 MiB memset outside the timed events); "
                    "every update regenerates its own rollout data"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / args.steps,
+                "episodes_dropped": dropped,
                 "note": "public API PPOTrainer.update()+metrics() with host syncs and a device->host read of the loss terms, "
                         "gradient norm, episode statistics and the per-episode records (what the reference prints) every update; "
                         "the environments live on the device, so the only per-update host inputs are kernel arguments (no tensor H2D)"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu_baseline,
         "phases_ms_per_update": {k: v["total_ms"] / args.steps for k, v in phases.items()},
-        "scaling_reference": scaling_ref,
+        "scaling_reference": scaling_ref, "extra_configs": extra, "fp32_path": fp32_path,
     }
+    if world > 1:
+        line.update(multi)
+        if single is not None:
+            line["single_gpu_same_workload"] = {"value": single["value"], "ms_per_step": single["ms_per_step_max_over_ranks"],
+                                                "steps": single["steps"], "unit": "env-steps/s"}
+            line["scaling_efficiency_like_for_like"] = single["ms_per_step_max_over_ranks"] / (dev_ms / args.steps)
     print(json.dumps(line), flush=True)
     dist.shutdown()
+
+
+class _SoloDist:
+    """dist-shaped no-ops for a world-1 trainer that runs inside a multi-rank job (every rank times its own copy)."""
+    @staticmethod
+    def barrier():
+        pass
+
+    @staticmethod
+    def all_reduce_max(x, dev):
+        return x
 
 
 def main():
@@ -418,9 +612,12 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scaling-reference", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip C3-on-one-GPU / C4 / C5 / fp32 / env-step records")
+    ap.add_argument("--hidden", type=int, default=64)
+    ap.add_argument("--hidden256", action="store_true", default=False, help="add the C5 (256-wide MLP) record to extra_configs")
     ap.add_argument("--grad-allreduce", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU gradient exchange: in-kernel NVLink peer-memory all-reduce, or NCCL between kernels")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"],
                     help="update GEMMs: bf16 = tcgen05 tensor cores (bf16 operands, fp32 accumulate), fp32 = CUDA cores")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -33,7 +33,7 @@ class NetT(C.Structure):
 
 class RolloutBufT(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("act", C.c_void_p), ("logp", C.c_void_p), ("val", C.c_void_p),
-                ("rew", C.c_void_p), ("done", C.c_void_p)]
+                ("rew", C.c_void_p), ("done", C.c_void_p), ("logits", C.c_void_p)]
 
 
 class CommT(C.Structure):
@@ -66,6 +66,7 @@ SIGNATURES = {
                               C.POINTER(EpLogT), C.c_uint32, C.c_void_p]),
     "drl_gae": (C.c_int, [C.POINTER(RolloutBufT), C.POINTER(NetT), C.c_int32, C.c_int32, C.c_float, C.c_float, f32p,
                           f32p, f32p, C.c_void_p]),
+    "drl_explained_variance": (C.c_int, [f32p, f32p, C.c_int64, f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "drl_permutation": (C.c_int, [u32p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
     "drl_adv_stats": (C.c_int, [C.POINTER(NetT), f32p, u32p, C.c_uint32, C.c_uint32, f32p, C.c_void_p, C.c_size_t,
                                 C.c_void_p]),
@@ -86,6 +87,7 @@ SIGNATURES = {
     "drl_comm_close": (C.c_int, [C.c_void_p]),
     "drl_comm_free": (C.c_int, [C.c_void_p]),
     "drl_selftest_umma": (C.c_int, [C.c_int32, C.c_int32, f32p, f32p, f32p, C.c_void_p]),
+    "drl_selftest_tanh": (C.c_int, [f32p, f32p, C.c_int64, C.c_void_p]),
     "drl_clip_adam": (C.c_int, [C.POINTER(NetT), f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_double, C.c_double, f32p, f32p, C.c_void_p]),
 }
@@ -99,19 +101,22 @@ def lib_path() -> str:
     return _build.SO
 
 
+ABI_VERSION = 2
+
+
 def lib() -> C.CDLL:
-    """Load (building first if the .so is absent) the CUDA library.  Raises if that is impossible."""
+    """Load the CUDA library, (re)building it first when it is absent or older than its sources and a compiler is
+    available (under an inter-process file lock, so that the ranks of one torchrun job do not race).  Raises if the
+    library can neither be found nor built."""
     global _LIB
     if _LIB is None:
-        path = _build.SO
-        if not os.path.exists(path):
-            path = _build.build()
+        path = _build.build_locked()
         L = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)   # AttributeError here = header/library mismatch: fail loudly
             fn.restype, fn.argtypes = res, args
-        if L.drl_abi_version() != 1:
-            raise DrlError(f"libdrl_b200 ABI version {L.drl_abi_version()} != 1")
+        if L.drl_abi_version() != ABI_VERSION:
+            raise DrlError(f"libdrl_b200 ABI version {L.drl_abi_version()} != {ABI_VERSION}")
         _LIB = L
     return _LIB
 

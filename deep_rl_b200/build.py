@@ -67,11 +67,35 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    link = [nvcc, "-shared", "-o", SO, *[obj for _, obj, _ in results], "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = SO + f".tmp{os.getpid()}"       # link to a private name, then rename: a concurrent dlopen never sees a partial file
+    link = [nvcc, "-shared", "-o", tmp, *[obj for _, obj, _ in results], "-gencode", "arch=compute_100a,code=sm_100a"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stderr)
         raise RuntimeError("nvcc link failed")
+    os.replace(tmp, SO)
+    return SO
+
+
+def build_locked() -> str:
+    """What the import path calls: returns the library path, rebuilding first if it is missing or stale.  The check and the
+    build run under an exclusive file lock (all ranks of a torchrun job import at once).  A stale library without a
+    compiler at hand (the GPU box always has one; a stripped deployment may not) is used as it is."""
+    import fcntl
+    os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if is_stale():
+                try:
+                    _nvcc()
+                except RuntimeError:
+                    if os.path.exists(SO):
+                        return SO
+                    raise
+                build()
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
     return SO
 
 

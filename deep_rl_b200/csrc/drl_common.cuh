@@ -76,7 +76,8 @@ struct Packed {
     static constexpr int ALL = W2P + 2 * H * H;
     // ---- tensor-core section (update_tc.cu), natural unit order, staged by one TMA bulk copy ----
     //   TC_W2 : bf16 [2][64 rows o][64 i] as two SW128 UMMA tiles (16 KB)
-    //   TC_W1 : fp32 [2][H][OW] (OW = 4 or 8, zero padded), TC_B1 / TC_B2 : fp32 [2][H]
+    //   TC_W1 : fp32 [2][H][OW] (OW = 4 or 8, zero padded) and TC_B1 : fp32 [2][H], both holding bf16-ROUNDED values (the
+    //           rollout's CUDA-core layer 1 then matches the update's layer-1 GEMM operands); TC_B2 : fp32 [2][H]
     //   TC_W4 : fp32 [A+1][H] (actor rows, then the critic row), TC_B4 : fp32 [4]
     static constexpr int OW = O <= 4 ? 4 : 8;
     static constexpr int TC_W2 = ALL;

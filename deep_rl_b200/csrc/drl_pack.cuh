@@ -19,7 +19,9 @@ __device__ __forceinline__ void packed_store(float* __restrict__ packed, int i, 
     if (r < H * O) {
         const int o = r / O, k = r % O;
         packed[P::W1T + (net * O + k) * H + perm_pos(o)] = v;
-        packed[P::TC_W1 + (net * H + o) * P::OW + k] = v;
+        // fp32 container, bf16-rounded value: the tensor-core rollout computes layer 1 on CUDA cores with exactly the operand
+        // values the update's layer-1 GEMM sees (TC_W1B below), so that log-probs recorded there and re-evaluated here agree
+        packed[P::TC_W1 + (net * H + o) * P::OW + k] = __bfloat162float(__float2bfloat16_rn(v));
         __nv_bfloat16* w1b = reinterpret_cast<__nv_bfloat16*>(packed + P::TC_W1B) + net * (2 * H * 8);
         w1b[o * 8 + k] = __float2bfloat16_rn(v);             // chunk 0, k < O  (x_hi)
         w1b[H * 8 + o * 8 + k] = __float2bfloat16_rn(v);     // chunk 1, k + 8  (x_lo)
@@ -28,7 +30,7 @@ __device__ __forceinline__ void packed_store(float* __restrict__ packed, int i, 
     r -= H * O;
     if (r < H) {
         packed[P::B1 + net * H + perm_pos(r)] = v;
-        packed[P::TC_B1 + net * H + r] = v;
+        packed[P::TC_B1 + net * H + r] = __bfloat162float(__float2bfloat16_rn(v));
         reinterpret_cast<__nv_bfloat16*>(packed + P::TC_W1B)[net * (2 * H * 8) + r * 8 + O] = __float2bfloat16_rn(v);   // ones column
         return;
     }
@@ -69,7 +71,7 @@ constexpr int STAT_PARTS = 512;      // max partial-sum CTAs per minibatch in dr
 constexpr int LOSS_TERMS = 8;
 
 struct WorkspaceLayout {
-    size_t counters, stat_partials, cta_sumsq, loss_partials, grad_partials, debug, total;
+    size_t counters, stat_partials, cta_sumsq, loss_partials, grad_partials, debug, ev_partials, total;
     int ppad;
 };
 inline WorkspaceLayout workspace_layout(int64_t P) {
@@ -80,7 +82,9 @@ inline WorkspaceLayout workspace_layout(int64_t P) {
     // squared-norm shares of the fused clip+Adam steps: their own region, the statistics of a later epoch may run on
     // another stream while a minibatch step is in flight
     w.cta_sumsq = w.stat_partials + sizeof(double) * MAX_MINIBATCHES * STAT_PARTS * 2;
-    w.loss_partials = w.cta_sumsq + sizeof(double) * 1024;
+    w.ev_partials = w.cta_sumsq + sizeof(double) * 1024;   // drl_explained_variance: [STAT_PARTS][4] doubles (counter word 12);
+                                                           // every region up to here has a size independent of P
+    w.loss_partials = w.ev_partials + sizeof(double) * STAT_PARTS * 4;
     w.grad_partials = w.loss_partials + sizeof(float) * MAX_GRAD_CTAS * LOSS_TERMS;
     w.debug = w.grad_partials + sizeof(float) * (size_t)MAX_GRAD_CTAS * w.ppad;   // 4 KB of cycle stamps (DRL_TC_DEBUG=1)
     w.total = w.debug + 4096;

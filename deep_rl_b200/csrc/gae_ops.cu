@@ -275,6 +275,56 @@ __global__ void __launch_bounds__(256) adv_stats_perm_kernel(const float* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Explained variance (ppo.py:194-195): 1 - Var(values - returns) / Var(values), unbiased variances over all n slots.
+// Each CTA sums its grid-strided slice in fp64, the last CTA folds the partials in a fixed order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) explained_variance_kernel(const float* __restrict__ values, const float* __restrict__ returns,
+                                                                  int64_t n, float* __restrict__ out, double* __restrict__ partials,
+                                                                  uint32_t* __restrict__ counter) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};    // sum y, sum y^2, sum d, sum d^2 with d = y - r (fp32 subtraction like torch)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float yf = __ldg(values + i), rf = __ldg(returns + i);
+        const double y = (double)yf, d = (double)(yf - rf);
+        acc[0] += y; acc[1] = fma(y, y, acc[1]); acc[2] += d; acc[3] = fma(d, d, acc[3]);
+    }
+    __shared__ double sh[4][8];
+    __shared__ bool is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double t = warp_sum(acc[q]);
+        if (lane == 0) sh[q][warp] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+        partials[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (uint32_t p = threadIdx.x; p < gridDim.x; p += 32)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[q] += __ldcg(&partials[(size_t)p * 4 + q]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[q] = warp_sum(t[q]);
+        if (threadIdx.x == 0) {
+            const double cnt = (double)n;
+            const double var_y = (t[1] - t[0] * (t[0] / cnt)) / (cnt - 1.0);
+            const double var_d = (t[3] - t[2] * (t[2] / cnt)) / (cnt - 1.0);
+            out[0] = var_y == 0.0 ? __int_as_float(0x7FC00000) : (float)(1.0 - var_d / var_y);
+            *counter = 0;
+        }
+    }
+}
+
 }  // namespace drl
 
 using namespace drl;
@@ -297,6 +347,21 @@ int drl_gae(const drl_rollout_buf_t* buf, const drl_net_t* net, int32_t T, int32
         gae_kernel<8, 16><<<blocks, 128, 0, st>>>(buf->rew, buf->done, buf->val, buf->obs, buf->act, buf->logp, T, N, gamma,
                                                  gae_lambda, adv_out, ret_out, rec_out);
     DRL_LAUNCH_CHECK("gae_kernel");
+    return DRL_OK;
+}
+
+int drl_explained_variance(const float* values, const float* returns, int64_t n, float* out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    DRL_REQUIRE(values && returns && out && workspace, "drl_explained_variance: NULL pointer");
+    DRL_REQUIRE(n >= 2, "drl_explained_variance: n=%lld", (long long)n);
+    const WorkspaceLayout w = workspace_layout(0);        // the regions used here do not depend on the parameter count
+    DRL_REQUIRE(workspace_bytes >= w.total, "drl_explained_variance: workspace %zu < %zu bytes", workspace_bytes, w.total);
+    uint32_t* counter = reinterpret_cast<uint32_t*>((char*)workspace + w.counters) + 12;
+    double* partials = reinterpret_cast<double*>((char*)workspace + w.ev_partials);
+    int64_t blocks = (n + 4095) / 4096;
+    if (blocks > STAT_PARTS) blocks = STAT_PARTS;
+    explained_variance_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(values, returns, n, out, partials, counter);
+    DRL_LAUNCH_CHECK("explained_variance_kernel");
     return DRL_OK;
 }
 

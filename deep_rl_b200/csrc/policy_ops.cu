@@ -71,11 +71,8 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ l
 template <int O, int A, int OP>
 int launch_forward(const float* packed, const float* obs, int64_t n, float* logits, float* value, cudaStream_t st) {
     const size_t smem = sizeof(float) * (Packed<O, A>::FWD + 4 + FWD_WARPS * (OBS_S + H1_S + OUT_S));
-    static bool configured = false;
-    if (!configured) {
-        DRL_CUDA(cudaFuncSetAttribute(policy_forward_kernel<O, A, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // per call: the attribute belongs to the current device / context, and the header promises re-entrancy across threads
+    DRL_CUDA(cudaFuncSetAttribute(policy_forward_kernel<O, A, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (n + TILE - 1) / TILE;
     int64_t blocks = (tiles + FWD_WARPS - 1) / FWD_WARPS;
     const int64_t cap = (int64_t)sm_count() * 4;

@@ -80,6 +80,10 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(drl_env_t env, c
                 float l[A];
 #pragma unroll
                 for (int a = 0; a < A; ++a) l[a] = out_s[lane * OUT_W + a];
+                if (buf.logits != nullptr) {
+#pragma unroll
+                    for (int a = 0; a < A; ++a) buf.logits[i0 * A + a] = l[a];
+                }
                 const uint64_t step = step0 + (uint64_t)t;
                 const uint4 r = philox_seeded(env.seed, gid, (uint32_t)step, (uint32_t)(step >> 32), TAG_ACTION);
                 float lp;

@@ -153,6 +153,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
 #pragma unroll
                 for (int qq = 0; qq < OP / 4; ++qq) o4[qq] = make_float4(obs[4 * qq], obs[4 * qq + 1], obs[4 * qq + 2], obs[4 * qq + 3]);
             }
+            // layer-1 input as the update's GEMM sees it: obs = hi + lo with both halves rounded to bf16 (update_tc.cu loader)
+#pragma unroll
+            for (int i = 0; i < OP; ++i) {
+                const float hi = __bfloat162float(__float2bfloat16_rn(obs[i]));
+                obs[i] = hi + __bfloat162float(__float2bfloat16_rn(obs[i] - hi));
+            }
 #pragma unroll
             for (int qq = 0; qq < OP / 4; ++qq)
                 *reinterpret_cast<float4*>(obs_s + er * OW + 4 * qq) = make_float4(obs[4 * qq], obs[4 * qq + 1], obs[4 * qq + 2], obs[4 * qq + 3]);
@@ -266,6 +272,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
 #pragma unroll
                     for (int j = 1; j < NSLOT; ++j) sacc += xch[(j * A + a) * TC_TILE + er];
                     l[a] = sacc + sB4[a];
+                }
+                if (buf.logits != nullptr) {
+#pragma unroll
+                    for (int a = 0; a < A; ++a) buf.logits[i0 * A + a] = l[a];
                 }
                 RO_STAMP(8);
                 const uint64_t step = step0 + (uint64_t)t;

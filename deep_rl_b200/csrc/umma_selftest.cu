@@ -5,7 +5,7 @@
 //   mode 1: D[128x64]  = A[128x64] . B[64x64]        A K-major SW128, B MN-major SW128     (dh1 = dz2 . W2)
 //   mode 2: D[128x128] = A[128x128]^T . B[128x128]   A, B MN-major SW128 tile pairs        (dW2 = dz2^T . h1)
 //   mode 3: D[128x16]  = A[128x128]^T . B[128x16]    A MN-major SW128 pair, B MN-major NS16 (dW1 / dW4 / db)
-#include "drl_umma.cuh"
+#include "drl_tc_common.cuh"
 
 namespace drl {
 
@@ -111,9 +111,22 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(int mode, int varian
     if (warp == 0) umma::tmem_dealloc(tmem, 128);
 }
 
+__global__ void __launch_bounds__(256) tanh_selftest_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = tanh_mufu(x[i]);
+}
+
 }  // namespace drl
 
 using namespace drl;
+
+extern "C" int drl_selftest_tanh(const float* x, float* y, int64_t n, void* stream) {
+    DRL_REQUIRE(x && y, "drl_selftest_tanh: NULL pointer");
+    if (n <= 0) return DRL_OK;
+    tanh_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, y, n);
+    DRL_LAUNCH_CHECK("tanh_selftest_kernel");
+    return DRL_OK;
+}
 
 extern "C" int drl_selftest_umma(int32_t mode, int32_t variant, const float* a, const float* b, float* d_out, void* stream) {
     DRL_REQUIRE(mode >= 0 && mode <= 3, "drl_selftest_umma: mode=%d", mode);

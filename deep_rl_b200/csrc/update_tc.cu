@@ -686,8 +686,10 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(tl.peer[tl.rank] + cl.flags[gen] + 4 * tid);
             const long long t0 = clock64();
             while (*f < tl.seq) {
-                if (clock64() - t0 > 40000000000ll) { if (tl.error_flag) *tl.error_flag = 1; break; }   // ~20 s: a peer is gone (start-up skew
-                                                                                                   // between ranks can reach seconds)
+                if (clock64() - t0 > 40000000000ll) {   // ~20 s: a peer is gone (start-up skew between ranks can reach seconds)
+                    if (tl.error_flag) { *reinterpret_cast<volatile int*>(tl.error_flag) = 1; __threadfence(); }
+                    break;
+                }
             }
             __threadfence_system();
         }
@@ -734,7 +736,10 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     }
     named_bar_sync(BAR_TAIL, TC_COMPUTE);
     const float coef = sbc[0];
-    for (int p = p_lo + tid; p < p_hi; p += TC_COMPUTE) {
+    // A peer that missed the all-reduce timeout left garbage in the summed gradient: skip the optimizer step on every CTA
+    // (the flag was written before the grid barrier above, so all CTAs agree; it is sticky, the host raises on its next read).
+    const bool peer_lost = multi && tl.error_flag != nullptr && *reinterpret_cast<volatile int*>(tl.error_flag) != 0;
+    for (int p = p_lo + tid; p < p_hi && !peer_lost; p += TC_COMPUTE) {
         const float gsc = (__ldcg(tl.grad_out + p) * ad.grad_scale) * coef;
         float m, v, wgt;
         if (p == p_first) { m = pre_m; v = pre_v; wgt = pre_w; }

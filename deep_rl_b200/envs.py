@@ -84,7 +84,7 @@ class VecEnv:
     """`num_envs` independent environments stepping in one kernel launch."""
 
     def __init__(self, env_id: str = "CartPole-v1", num_envs: int = 1, seed: int = 1, env_gid0: int = 0,
-                 device: Optional[torch.device] = None, log_capacity: int = 1 << 16):
+                 device: Optional[torch.device] = None, log_capacity: Optional[int] = None):
         if env_id not in ENV_KINDS:
             raise ValueError(f"unsupported env_id {env_id!r}; supported: {sorted(ENV_KINDS)}")
         _lib.require_cuda()
@@ -102,6 +102,11 @@ class VecEnv:
         self.elapsed = torch.zeros(N, dtype=torch.int32, device=self.device)
         self.ep_ret = torch.zeros(N, dtype=torch.float32, device=self.device)
         self.ep_len = torch.zeros(N, dtype=torch.int32, device=self.device)
+        if log_capacity is None:
+            # enough for every episode that can finish between two drains of a 256-step rollout (an untrained CartPole policy
+            # lasts >= 8 steps), 24 B per entry, bounded at 4 Mi entries; beyond it entries are dropped and COUNTED
+            # (metrics()["episodes_dropped"])
+            log_capacity = min(max(1 << 16, N * 32), 1 << 22)
         self.log = EpisodeLog(log_capacity, self.device)
         self.step_count = 0          # global step index fed to the Philox counter
         self._seed = int(seed)

@@ -7,11 +7,17 @@ are the two additions.  The loop keeps the shape of ppo.py:105
         lr anneal                          ppo.py:107-108   (host scalar)
         rollout of num_steps               ppo.py:110-141   drl_rollout        (1 launch)
         GAE + returns (+ record packing)   ppo.py:144-151   drl_gae            (1 launch)
+        permutations of all epochs         ppo.py:155       drl_permutation      (side stream, during the rollout)
+        advantage statistics per epoch     ppo.py:169       drl_adv_stats_perm   (side stream, one epoch ahead)
         for epoch in range(update_epochs):
-            permutation                    ppo.py:155       drl_permutation + drl_adv_stats
-            for each minibatch:            ppo.py:156-192   drl_ppo_minibatch_grad
-                                                            [NCCL all-reduce of the flat gradient]
-                                                            drl_clip_adam
+            for each minibatch:            ppo.py:156-192   drl_ppo_minibatch_update[_dist]: gather + loss + backward + fold +
+                                                            [in-kernel NVLink all-reduce] + clip + Adam, ONE cooperative launch
+                                           (fp32 / NCCL variant: drl_ppo_minibatch_grad, NCCL all-reduce, drl_clip_adam)
+
+Precision: `update_precision="auto"` runs the tcgen05 (bf16 operands, fp32 accumulate) kernels from 2,048 envs per rank and
+the strict fp32 CUDA-core kernels below (the reference shape, N = 1, is fp32 end to end); the rollout always follows the
+update so that the log-probs and values it records are re-evaluated with the same numerics (ratio = 1, approx_kl = 0 at
+the first minibatch of an update).
 
 Run as a script:  python -m deep_rl_b200.ppo [--num-envs N] [--total-timesteps K] ...
 """
@@ -49,15 +55,25 @@ class PPOConfig:
     hidden: int = 64
     num_minibatches: int = 4     # reference: minibatch_size = num_steps // 4
     anneal_lr: bool = True
-    rollout_precision: str = "auto"  # "bf16": tcgen05 rollout (32-128 envs per CTA); "fp32": CUDA-core rollout; "auto": bf16 when
-                                     # the update is bf16 and there are at least 2048 envs
+    rollout_precision: str = "auto"  # "bf16": tcgen05 rollout (32-128 envs per CTA); "fp32": CUDA-core rollout; "auto": the
+                                     # precision of the update (same numerics when log-probs / values are re-evaluated)
     overlap_streams: bool = True     # permutations (during the rollout) and advantage statistics of later epochs (during the
                                      # minibatch steps of earlier ones) run on a second CUDA stream
     global_adv_stats: bool = False   # multi-GPU: normalise advantages with the statistics of the GLOBAL minibatch (one extra
                                      # all-reduce of 3 numbers per minibatch, once per update) instead of per-rank ones
     grad_allreduce: str = "peer"     # multi-GPU gradient exchange: "peer" = one-shot all-reduce over NVLink peer memory inside
                                      # the gradient kernel (bf16 update only), "nccl" = NCCL all-reduce between kernels
-    update_precision: str = "bf16"   # "bf16": tcgen05 tensor-core update (bf16 operands, fp32 accumulate); "fp32": CUDA-core update
+    update_precision: str = "auto"   # "bf16": tcgen05 tensor-core update (bf16 operands, fp32 accumulate); "fp32": CUDA-core
+                                     # update; "auto": bf16 from 2048 envs per rank (minibatches of >= 64k samples), else fp32
+    debug_logits: bool = False       # record the logits every action was sampled from ([T][N][A] plane, parity tests)
+
+    def resolved_update_precision(self) -> str:
+        if self.update_precision == "auto":
+            return "bf16" if (self.num_envs >= 2048 or self.hidden != 64) else "fp32"
+        return self.update_precision
+
+    def resolved_rollout_precision(self) -> str:
+        return self.resolved_update_precision() if self.rollout_precision == "auto" else self.rollout_precision
 
     @property
     def batch_size(self) -> int:             # samples per rank per update
@@ -119,8 +135,10 @@ class PPOTrainer:
         self.dones = torch.zeros((T + 1, N), dtype=u8, device=dev)
         self.advantages = torch.zeros((T + 1, N), dtype=f32, device=dev)
         self.returns = torch.zeros((T + 1, N), dtype=f32, device=dev)
+        self.logits = torch.zeros((T, N, self.env.num_actions), dtype=f32, device=dev) if cfg.debug_logits else None
         self.buf = _lib.RolloutBufT(self.observations.data_ptr(), self.actions.data_ptr(), self.log_probs.data_ptr(),
-                                    self.values.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr())
+                                    self.values.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(),
+                                    _lib.ptr(self.logits))
         B = cfg.batch_size
         self.RW = self.L.drl_record_width(C.byref(self.net))
         self.records = torch.zeros((B, self.RW), dtype=f32, device=dev)
@@ -148,14 +166,15 @@ class PPOTrainer:
         self.ws_bytes = int(self.L.drl_workspace_bytes(C.byref(self.net)))
         self.workspace = torch.zeros(self.ws_bytes, dtype=u8, device=dev)
         self.coef = _lib.PpoCoefT(cfg.clip_coef, cfg.ent_coef, cfg.vf_coef)
-        if cfg.update_precision not in ("bf16", "fp32"):
+        if cfg.update_precision not in ("auto", "bf16", "fp32"):
             raise ValueError(f"update_precision={cfg.update_precision!r}")
-        self.grad_flags = 1 if cfg.update_precision == "bf16" else 0
         if cfg.rollout_precision not in ("auto", "bf16", "fp32"):
             raise ValueError(f"rollout_precision={cfg.rollout_precision!r}")
-        tc_rollout = cfg.rollout_precision == "bf16" or (cfg.rollout_precision == "auto" and cfg.update_precision == "bf16"
-                                                         and N >= 2048)
-        self.rollout_flags = 1 if tc_rollout else 0
+        self.update_precision = cfg.resolved_update_precision()
+        self.rollout_precision = cfg.resolved_rollout_precision()
+        self.grad_flags = 1 if self.update_precision == "bf16" else 0
+        self.rollout_flags = 1 if self.rollout_precision == "bf16" else 0
+        self._ev_out = torch.zeros(1, dtype=f32, device=dev)
         self.adam_step = 0
         self.update_idx = 0
         self.global_step = 0       # env steps taken on this rank's envs x world (reference counter at N=1)
@@ -258,6 +277,9 @@ class PPOTrainer:
         cfg = self.cfg
         B, M = cfg.batch_size, cfg.minibatch_size
         net = C.byref(self.net)
+        if self.world > 1 and self.peer is None and not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            raise _lib.DrlError("world > 1 needs an initialised torch.distributed process group for the gradient all-reduce "
+                                "(deep_rl_b200.dist.init_from_env); without it the gradient would only be scaled by 1/world")
         if not self._perms_scheduled:
             self.schedule_permutations()
         self._perms_scheduled = False
@@ -333,12 +355,18 @@ class PPOTrainer:
         else:
             n, sum_ret, sum_len, entries = self.env.log.drain(with_entries=with_episode_log)
         lt = self._h_terms.tolist()
-        if self.peer is not None and int(self.peer.error_flag.item()) != 0:
-            raise _lib.DrlError("a peer rank did not arrive at the in-kernel all-reduce within the timeout")
+        self.check_peers()
         return {"loss": lt[0], "pg_loss": lt[1], "v_loss": lt[2], "entropy": lt[3], "approx_kl": lt[4],
-                "clipfrac": lt[5], "grad_norm": lt[8], "episodes": n,
+                "clipfrac": lt[5], "grad_norm": lt[8], "episodes": n, "episodes_dropped": max(0, n - self.env.log.cap),
                 "mean_return": (sum_ret / n) if n else float("nan"), "mean_length": (sum_len / n) if n else float("nan"),
                 "episode_log": entries}
+
+    def check_peers(self) -> None:
+        """Raises if a peer rank missed the in-kernel all-reduce (the kernels skip the optimizer step from then on).
+        Synchronises: called from metrics() and state_dict(), which synchronise anyway."""
+        if self.peer is not None and int(self.peer.error_flag.item()) != 0:
+            raise _lib.DrlError("a peer rank did not arrive at the in-kernel all-reduce within the timeout; "
+                                "optimizer steps have been skipped since")
 
     def _d_terms_src(self) -> torch.Tensor:
         # loss terms of the last minibatch (8 floats) followed by the pre-clip gradient norm: rows are contiguous
@@ -349,18 +377,27 @@ class PPOTrainer:
         """Everything needed to resume bit-identically: model + optimizer (ppo.py:86-90), counters, env state and the carried
         reward / done slot of the one-slot-shifted storage (ppo.py:93-98).  Tensors are CPU copies (synchronises)."""
         e = self.env
+        self.check_peers()
         return {"model": {k: v.detach().cpu().clone() for k, v in self.agent.state_dict().items()},
                 "exp_avg": self.exp_avg.cpu().clone(), "exp_avg_sq": self.exp_avg_sq.cpu().clone(),
                 "adam_step": self.adam_step, "update_idx": self.update_idx, "global_step": self.global_step,
                 "env": {"state": e.state.cpu().clone(), "elapsed": e.elapsed.cpu().clone(), "ep_ret": e.ep_ret.cpu().clone(),
                         "ep_len": e.ep_len.cpu().clone(), "step_count": e.step_count},
                 "carry": {"rewards0": self.rewards[0].cpu().clone(), "dones0": self.dones[0].cpu().clone()},
-                "config": {"env_id": self.cfg.env_id, "num_envs": self.cfg.num_envs, "num_steps": self.cfg.num_steps, "seed": self.cfg.seed}}
+                "config": self._resume_key()}
+
+    def _resume_key(self) -> Dict[str, object]:
+        """Everything a bit-identical resume depends on besides the tensors: shapes, Philox key / counters' owner, numerics."""
+        c = self.cfg
+        return {"env_id": c.env_id, "num_envs": c.num_envs, "num_steps": c.num_steps, "seed": c.seed, "hidden": c.hidden,
+                "rank": self.rank, "world": self.world, "update_precision": self.update_precision,
+                "rollout_precision": self.rollout_precision}
 
     def load_state_dict(self, sd: Dict[str, object]) -> None:
-        c = sd["config"]
-        if (c["env_id"], c["num_envs"], c["num_steps"]) != (self.cfg.env_id, self.cfg.num_envs, self.cfg.num_steps):
-            raise ValueError(f"checkpoint was taken with {c}, this trainer runs {self.cfg.env_id} x {self.cfg.num_envs} x {self.cfg.num_steps}")
+        c, mine = sd["config"], self._resume_key()
+        diff = {k: (c.get(k), v) for k, v in mine.items() if c.get(k) != v}
+        if diff:
+            raise ValueError(f"checkpoint does not match this trainer (checkpoint, trainer): {diff}")
         self.agent.load_state_dict(sd["model"])
         self.agent.sync()
         self.exp_avg.copy_(sd["exp_avg"])
@@ -374,10 +411,11 @@ class PPOTrainer:
         self._perms_scheduled = False
 
     def explained_variance(self) -> float:
-        """ppo.py:194-195 (computed over all T+1 slots like the reference)."""
-        y, r = self.values.flatten(), self.returns.flatten()
-        var_y = torch.var(y)
-        return float("nan") if float(var_y) == 0 else float(1 - torch.var(y - r) / var_y)
+        """ppo.py:194-195 over all T+1 slots like the reference: drl_explained_variance (one launch, synchronises for the read)."""
+        _lib.check(self.L.drl_explained_variance(self.values.data_ptr(), self.returns.data_ptr(), self.values.numel(),
+                                                 self._ev_out.data_ptr(), self.workspace.data_ptr(), self.ws_bytes,
+                                                 _lib.stream_ptr()))
+        return float(self._ev_out.item())
 
 
 def train(cfg: PPOConfig, quiet: bool = False, rank: int = 0, world: int = 1) -> PPOTrainer:

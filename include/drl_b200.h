@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRL_ABI_VERSION 1
+#define DRL_ABI_VERSION 2
 
 enum { DRL_ENV_CARTPOLE = 0, DRL_ENV_ACROBOT = 1, DRL_ENV_MOUNTAINCAR = 2 };   /* gym ids CartPole-v1, Acrobot-v1, MountainCar-v0 */
 enum { DRL_OK = 0, DRL_ERR_ARG = -1, DRL_ERR_UNSUPPORTED = -2, DRL_ERR_CUDA = -3 };
@@ -75,6 +75,8 @@ typedef struct {
     float*   val;   /* [T+1][N] */
     float*   rew;   /* [T+1][N] */
     uint8_t* done;  /* [T+1][N] */
+    float*   logits; /* optional debug plane [T][N][A]: the logits each action was sampled from (NULL = not recorded);
+                        lets a test feed the kernel's own logits to the oracle sampler and demand identical actions */
 } drl_rollout_buf_t;
 
 typedef struct {
@@ -126,6 +128,11 @@ int drl_rollout(const drl_env_t* env, const drl_net_t* net, const float* packed,
  * rec_out (nullable) is [T*N][RW]: obs[0..O), then at the last four words logp, adv, val, act(int32 bits). */
 int drl_gae(const drl_rollout_buf_t* buf, const drl_net_t* net, int32_t T, int32_t N, float gamma, float gae_lambda,
             float* adv_out, float* ret_out, float* rec_out, void* stream);
+
+/* ---- explained variance diagnostic, ppo.py:194-195: 1 - Var(values - returns) / Var(values) over all n = (T+1)*N slots,
+ * unbiased variances like torch.var; NaN when Var(values) == 0.  out [1]; fp64 accumulation, fixed-order fold. ---- */
+int drl_explained_variance(const float* values, const float* returns, int64_t n, float* out, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* ---- minibatch permutation, ppo.py:155 ---- */
 int drl_permutation(uint32_t* idx_out /*[B]*/, uint32_t B, uint64_t seed, uint32_t epoch_ctr, uint32_t rank, void* stream);
@@ -195,6 +202,9 @@ int drl_clip_adam(const drl_net_t* net, float* params, const float* grad, float*
 /* ---- diagnostics: runs one tcgen05.mma operand-layout combination of the update kernel on caller matrices
  * (fp32 row-major in, fp32 row-major out; operands are rounded to bf16).  See csrc/umma_selftest.cu. ---- */
 int drl_selftest_umma(int32_t mode, int32_t variant, const float* a, const float* b, float* d_out, void* stream);
+/* y[i] = tanh.approx.f32(x[i]) -- the SFU instruction the tensor-core kernels use for their activations; lets the
+ * bf16-emulating oracle (oracle/ppo_oracle.py) reproduce the kernels' activations bit for bit. */
+int drl_selftest_tanh(const float* x, float* y, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -164,3 +164,110 @@ def rollout(flat_np, env: clib.OracleVecEnv, obs0: np.ndarray, T: int, H: int, c
             for i in np.nonzero(d)[0]:
                 fin.append((env.step_count - 1, int(i), float(info["final_return"][i]), int(info["final_length"][i])))
     return dict(obs=obs, val=val, act=act, logp=logp, rew=rew, done=done, logits=logits_all, episodes=fin)
+
+
+# ----------------------------------------------------------------------------------------------
+# bf16-emulating restatement of the tensor-core kernels' numerics (deep_rl_b200/csrc/update_tc.cu, rollout_tc.cu).
+# The GEMM operands are rounded to bf16 at exactly the points where the kernels write their shared-memory operand
+# tiles (observation hi + lo halves, W1 | b1, h1, W2, h2 / dout for dW4, dz2, dz1); products of bf16 values are exact
+# in fp32 and the accumulation is done in float64 here (fp32 in tensor memory on the GPU), everything else is fp32.
+# `tanh_fn` is the activation: the kernels use the SFU instruction tanh.approx.f32, which has no CPU equivalent, so the
+# GPU tests pass the device's own elementwise tanh.approx (drl_selftest_tanh); torch.tanh gives the idealised variant.
+# With the same activation function the kernels must agree with this oracle to ~1e-4 (fp32 accumulation order),
+# two orders of magnitude tighter than their distance to the fp32 reference maths (which is bf16 rounding noise).
+# ----------------------------------------------------------------------------------------------
+def _bf(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _mm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """fp32 <- exact products, float64 accumulation."""
+    return (a.double() @ b.double()).float()
+
+
+def _net_forward_bf16(p, pre: str, obs: torch.Tensor, tanh_fn):
+    W1, b1, W2, b2 = p[pre + ".0.weight"], p[pre + ".0.bias"], p[pre + ".2.weight"], p[pre + ".2.bias"]
+    W4, b4 = p[pre + ".4.weight"], p[pre + ".4.bias"]
+    hi = _bf(obs)
+    lo = _bf(obs - hi)
+    W1b = _bf(W1)
+    z1 = ((hi.double() @ W1b.double().T) + _bf(b1).double() + (lo.double() @ W1b.double().T)).float()
+    h1 = _bf(tanh_fn(z1))
+    z2 = _mm(h1, _bf(W2).T)
+    h2 = tanh_fn(z2 + b2)
+    out = _mm(h2, W4.T) + b4
+    return dict(hi=hi, lo=lo, h1=h1, h2=h2, out=out, W2b=_bf(W2), W4=W4)
+
+
+def mlp_forward_bf16_emulated(flat, obs, O: int, H: int, A: int, tanh_fn=torch.tanh):
+    """(logits, value) as rollout_tc_kernel / ppo_grad_tc_kernel compute them."""
+    p = split_flat(torch.as_tensor(np.asarray(flat, dtype=np.float32)), O, H, A)
+    x = torch.as_tensor(np.asarray(obs, dtype=np.float32))
+    with torch.no_grad():
+        a = _net_forward_bf16(p, "actor", x, tanh_fn)
+        c = _net_forward_bf16(p, "critic", x, tanh_fn)
+    return a["out"], c["out"].squeeze(-1)
+
+
+def minibatch_grad_bf16_emulated(flat_np, obs, act, logp_old, adv, val_old, O, H, A, adv_mean: float, adv_std: float,
+                                 c: Coeffs = Coeffs(), tanh_fn=torch.tanh):
+    """Loss terms [loss, pg, v, entropy, approx_kl, clipfrac] and the flat gradient (state_dict order) of one minibatch,
+    with the closed-form backward and the bf16 rounding points of ppo_grad_tc_kernel."""
+    t = lambda x, dt=torch.float32: torch.as_tensor(np.asarray(x), dtype=dt)
+    p = split_flat(t(flat_np), O, H, A)
+    x, act, logp_old, adv, val_old = t(obs), t(act, torch.int64), t(logp_old), t(adv), t(val_old)
+    M = x.shape[0]
+    inv_m = torch.tensor(1.0 / M, dtype=torch.float32)
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+    grads = {}
+    with torch.no_grad():
+        # ---- actor ----
+        a = _net_forward_bf16(p, "actor", x, tanh_fn)
+        out = a["out"]
+        m = out.max(-1, keepdim=True).values
+        lse = m + torch.log(torch.exp(out - m).sum(-1, keepdim=True))
+        lp = out - lse
+        pr = torch.exp(lp)
+        ent = -(pr * lp).sum(-1)
+        new_logp = lp.gather(-1, act.unsqueeze(-1)).squeeze(-1)
+        nadv = (adv - f32(adv_mean)) * (f32(1.0) / (f32(adv_std) + f32(1e-8)))
+        logratio = new_logp - logp_old
+        ratio = torch.exp(logratio)
+        pg1 = -nadv * ratio
+        pg2 = -nadv * torch.clamp(ratio, 1.0 - c.clip_coef, 1.0 + c.clip_coef)
+        dpg = torch.where(pg1 >= pg2, pg1, torch.zeros_like(pg1))
+        onehot = torch.nn.functional.one_hot(act, A).float()
+        d_act = inv_m * (dpg.unsqueeze(-1) * (onehot - pr) + f32(c.ent_coef) * pr * (lp + ent.unsqueeze(-1)))
+        pg_loss = torch.maximum(pg1, pg2).sum() * inv_m
+        entropy = ent.sum() * inv_m
+        approx_kl = ((ratio - 1.0) - logratio).sum() * inv_m
+        clipfrac = ((ratio - 1.0).abs() > c.clip_coef).float().sum() * inv_m
+        # ---- critic ----
+        cr = _net_forward_bf16(p, "critic", x, tanh_fn)
+        v = cr["out"].squeeze(-1)
+        ret = adv + val_old
+        vd = v - ret
+        vu = vd * vd
+        vdiff = v - val_old
+        vcd = (val_old + torch.clamp(vdiff, -c.clip_coef, c.clip_coef)) - ret
+        vcl = vcd * vcd
+        gcl = torch.where((vdiff >= -c.clip_coef) & (vdiff <= c.clip_coef), vcd, torch.zeros_like(vcd))
+        gv = torch.where(vu > vcl, vd, torch.where(vcl > vu, gcl, 0.5 * (vd + gcl)))
+        d_cri = (f32(c.vf_coef) * gv * inv_m).unsqueeze(-1)
+        v_loss = 0.5 * torch.maximum(vu, vcl).sum() * inv_m
+        # ---- backward, identical for both nets ----
+        for pre, f, d in (("actor", a, d_act), ("critic", cr, d_cri)):
+            h1, h2, W2b, W4 = f["h1"], f["h2"], f["W2b"], f["W4"]
+            dz2 = _bf((d @ W4) * (1.0 - h2 * h2))
+            dh1 = _mm(dz2, W2b)
+            dz1 = _bf(dh1 * (1.0 - h1 * h1))
+            grads[pre + ".0.weight"] = _mm(dz1.T, f["hi"]) + _mm(dz1.T, f["lo"])
+            grads[pre + ".0.bias"] = dz1.double().sum(0).float()
+            grads[pre + ".2.weight"] = _mm(dz2.T, h1)
+            grads[pre + ".2.bias"] = dz2.double().sum(0).float()
+            grads[pre + ".4.weight"] = _mm(_bf(d).T, _bf(h2))
+            grads[pre + ".4.bias"] = d.double().sum(0).float()
+    loss = pg_loss - c.ent_coef * entropy + v_loss * c.vf_coef
+    flat_grad = torch.cat([grads[n].reshape(-1) for n in PARAM_NAMES]).numpy().copy()
+    terms = [float(loss), float(pg_loss), float(v_loss), float(entropy), float(approx_kl), float(clipfrac)]
+    return terms, flat_grad

@@ -114,6 +114,8 @@ def main():
         "hyper": np.array([g["gamma"], g["gae_lambda"], g["learning_rate"], g["clip_coef"], g["ent_coef"],
                            g["vf_coef"], g["max_grad_norm"], g["num_steps"], g["num_updates"], g["minibatch_size"],
                            g["update_epochs"], g["seed"]], dtype=np.float64),
+        # ppo.py:194-195 as the script leaves it after the last update (values / returns of update 155 are stored below)
+        "explained_var": np.array(float(g["explained_var"]), dtype=np.float64),
     }
     for upd, d in rec["gae"].items():
         for k, v in d.items():

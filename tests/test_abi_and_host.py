@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     nm = subprocess.run(["nm", "-D", "--defined-only", L.lib_path()], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (drl_[a-z_0-9]+)", nm))
     assert declared <= exported
-    assert lib.drl_abi_version() == 1
+    assert lib.drl_abi_version() == 2
 
 
 def test_library_is_sm100a_only():

@@ -428,6 +428,82 @@ def test_tc_minibatch_grad_vs_torch_oracle(O, A, B, M):
         assert abs(terms[5] - t32[5]) < 0.02       # clip fraction agrees with the fp32 path
 
 
+def _gpu_tanh(x: torch.Tensor) -> torch.Tensor:
+    """The device's tanh.approx.f32 (activation of the tensor-core kernels), for the bf16-emulating oracle."""
+    L = _lib()
+    xd = x.detach().to(_dev(), torch.float32).contiguous()
+    yd = torch.empty_like(xd)
+    L.check(L.lib().drl_selftest_tanh(xd.data_ptr(), yd.data_ptr(), xd.numel(), L.stream_ptr()))
+    return yd.cpu().reshape(x.shape)
+
+
+def _assert_per_tensor(grad, want, O, A, tol, floor=1e-3):
+    """Relative L2 error of every one of the twelve gradient tensors (a wrong block would hide in the global norm); the
+    denominator is floored at `floor` x the whole-gradient norm so that a near-zero tensor cannot blow the ratio up."""
+    off, worst = 0, ("", 0.0)
+    total = float(np.linalg.norm(want))
+    for name, shp in zip(po.PARAM_NAMES, po.param_shapes(O, 64, A)):
+        n = int(np.prod(shp))
+        e = float(np.linalg.norm(grad[off:off + n] - want[off:off + n]) / max(np.linalg.norm(want[off:off + n]), floor * total))
+        assert e < tol, (name, e)
+        worst = max(worst, (name, e), key=lambda t: t[1])
+        off += n
+    return worst
+
+
+def test_selftest_tanh_is_the_sfu_instruction():
+    x = torch.linspace(-6, 6, 100_001)
+    y = _gpu_tanh(x)
+    assert float((y - torch.tanh(x)).abs().max()) < 1.5e-3          # tanh.approx.f32: ~2^-11 relative
+    assert torch.equal(y, _gpu_tanh(x)) and float(y.abs().max()) <= 1.0
+
+
+@pytest.mark.parametrize("O,A,B,M", [(4, 2, 4096, 1024), (6, 3, 3000, 750), (4, 2, 100_000, 25_000), (4, 2, 70, 70), (4, 2, 129, 129), (2, 3, 2000, 500)])
+def test_tc_minibatch_grad_vs_bf16_emulating_oracle(O, A, B, M):
+    """ppo_grad_tc_kernel against the oracle that rounds the GEMM operands to bf16 at the kernel's own rounding points and uses
+    the device's tanh.approx: every gradient tensor within 2e-3 relative L2, loss terms within 1e-4 -- 50x tighter than the
+    distance to the fp32 maths (test_tc_minibatch_grad_vs_torch_oracle), so an off-by-20 % bias block cannot hide."""
+    rng = np.random.default_rng(B)
+    RW = 8 if O <= 4 else 16
+    params = _rand_params(O, A, seed=5)
+    obs = rng.normal(size=(B, O)).astype(np.float32)
+    act = rng.integers(0, A, size=B)
+    logits, v = po.mlp_forward(torch.tensor(params), torch.tensor(obs), O, 64, A)
+    logp_all = torch.log_softmax(logits, -1).numpy()
+    logp_old = (logp_all[np.arange(B), act] + rng.normal(scale=0.15, size=B)).astype(np.float32)
+    val_old = (v.numpy() + rng.normal(scale=0.3, size=B)).astype(np.float32)
+    adv = rng.normal(size=B).astype(np.float32) * 2 + 0.3
+    rec = _make_records(obs, act, logp_old, adv, val_old, O, RW)
+    idx = clib.permutation(B, 3, 1, 0)
+    for k in range(min(2, B // M)):
+        sel = idx[k * M:(k + 1) * M].astype(np.int64)
+        grad, terms, st = _grad_gpu(params, rec, idx, k * M, M, O, A, flags=1)
+        wt, wg = po.minibatch_grad_bf16_emulated(params, obs[sel], act[sel], logp_old[sel], adv[sel], val_old[sel], O, 64, A,
+                                                 float(st[k, 0]), float(st[k, 1]), tanh_fn=_gpu_tanh)
+        worst = _assert_per_tensor(grad, wg, O, A, tol=2e-3)
+        print(f"O={O} B={B} mb={k}: whole-gradient rel L2 vs emulating oracle {_rel_l2(grad, wg):.2e}, worst tensor {worst}")
+        assert _rel_l2(grad, wg) < 1e-3
+        np.testing.assert_allclose(terms[:6], wt, rtol=1e-4, atol=2e-5)
+
+
+def test_tc_minibatch_grad_vs_bf16_emulation_on_reference_golden(golden):
+    """Same bar on the reference's own first update (its observations, actions, log-probs, advantages, permutations)."""
+    g = golden
+    rec = _make_records(g["u0_observations"][:128], g["u0_actions"][:128], g["u0_log_probs"][:128],
+                        g["u0_advantages"][:128], g["u0_values"][:128], 4, 8)
+    params = g["init_params"]
+    for i in range(16):
+        perm = g["perms"][i // 4]
+        sel = perm[(i % 4) * 32:(i % 4) * 32 + 32]
+        grad, terms, st = _grad_gpu(params, rec, perm, (i % 4) * 32, 32, 4, 2, flags=1)
+        wt, wg = po.minibatch_grad_bf16_emulated(params, g["u0_observations"][:128][sel], g["u0_actions"][:128][sel],
+                                                 g["u0_log_probs"][:128][sel], g["u0_advantages"][:128][sel], g["u0_values"][:128][sel],
+                                                 4, 64, 2, float(st[i % 4, 0]), float(st[i % 4, 1]), tanh_fn=_gpu_tanh)
+        _assert_per_tensor(grad, wg, 4, 2, tol=2e-3)
+        np.testing.assert_allclose(terms[:6], wt, rtol=1e-4, atol=2e-5)
+        params = g["mb_params_after"][i]
+
+
 def test_tc_minibatch_grad_deterministic_and_linear():
     O, A, B = 4, 2, 131_072
     rng = np.random.default_rng(1)
