@@ -314,13 +314,13 @@ def _hbm_rooflines(env_id, envs, T, E, phases, peaks):
     return out
 
 
-def _env_step_roofline(env_id, dev, peaks, n_envs=1 << 20, steps=20):
+def _env_step_roofline(env_id, dev, peaks, n_envs=1 << 22, steps=20):
     """One-off timing of the stand-alone env_step_kernel (drl_env_step: state in HBM) on n_envs environments."""
     import torch
     import deep_rl_b200 as drl
     env = drl.make(env_id, num_envs=n_envs, seed=3, device=dev)
     env.reset()
-    act = torch.zeros(n_envs, dtype=torch.int32, device=dev)
+    act = torch.randint(0, env.num_actions, (n_envs,), dtype=torch.int32, device=dev)
     import ctypes as C
     from deep_rl_b200 import _lib
     call = lambda k: _lib.check(env.L.drl_env_step(C.byref(env.struct), k, act.data_ptr(), env._obs.data_ptr(), env._rew.data_ptr(),
@@ -338,9 +338,8 @@ def _env_step_roofline(env_id, dev, peaks, n_envs=1 << 20, steps=20):
     gbs = nbytes / (ms * 1e-3) / 1e9
     return {"kernel": "env_step_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
             "bytes_per_launch": nbytes, "launch_ms": ms, "per": "env step", "envs": n_envs,
-            "note": "stand-alone drl_env_step (fp64 state read + written in HBM every step; 1 Mi envs, back-to-back launches, "
-                    "working set below the L2 size, so this is an upper bound on the HBM-resident rate); the training loop uses "
-                    "the fused rollout, whose state lives in registers"}
+            "note": "stand-alone drl_env_step (fp64 state read + written in HBM every step; 4 Mi envs = 394 MB per launch, larger than "
+                    "the L2; random actions); the training loop uses the fused rollout, whose state lives in registers"}
 
 
 def _run_config(name, env_id, envs, T, hidden, steps, warm, rank, world, dev, flush, dist, peaks, precision="auto", grad_allreduce="peer"):

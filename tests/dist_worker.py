@@ -15,7 +15,7 @@ from deep_rl_b200 import dist  # noqa: E402
 
 def run(mode, rank, world, envs, updates, global_stats=False):
     cfg = drl.PPOConfig(num_envs=envs, num_steps=32, seed=3, total_timesteps=envs * 32 * world * 16, grad_allreduce=mode,
-                        global_adv_stats=global_stats)
+                        global_adv_stats=global_stats, update_precision="bf16")      # the in-kernel exchange is part of the tcgen05 kernel
     tr = drl.PPOTrainer(cfg, rank=rank, world=world)
     assert (tr.peer is not None) == (mode == "peer")
     for _ in range(updates):

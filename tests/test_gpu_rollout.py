@@ -26,7 +26,8 @@ def _check_rollout(env_id, N, T, seed, sub=None, rounds=2, tc=False):
          log-probs (SURVEY hard part 2: identical logits + identical Philox counter => identical action),
        * those logits and val[t] must equal the oracle forward on the kernel's stored obs[t]: the fp32 torch oracle for
          the CUDA-core kernel (2e-5); for the tensor-core kernel the bf16-emulating oracle with the device's tanh.approx
-         (2e-4; the fp32 oracle is kept as the loose outer bound, 3e-2),
+         (5e-4: layer 1 runs as fp32 FMAs here and as a GEMM in the oracle, so about one h1 element in 10^4 rounds to the
+         neighbouring bf16 value, which moves a value by up to ~2e-4; the fp32 oracle is kept as the loose outer bound, 3e-2),
        * the oracle env driven by the kernel's actions must reproduce obs/rew/done (<= 1e-6 per step),
          auto-resets (Philox reset draws) and the episode log included."""
     import deep_rl_b200 as drl
@@ -53,8 +54,9 @@ def _check_rollout(env_id, N, T, seed, sub=None, rounds=2, tc=False):
             if tc:      # one batched emulated forward over the whole rollout
                 el, ev = po.mlp_forward_bf16_emulated(flat.numpy(), obs.reshape(-1, O), O, 64, A, tanh_fn=_gpu_tanh)
                 el, ev = el.numpy().reshape(T + 1, N, A), ev.numpy().reshape(T + 1, N)
-                np.testing.assert_allclose(val, ev, rtol=0, atol=2e-4, err_msg="value vs bf16-emulating oracle")
-                np.testing.assert_allclose(klog, el[:T], rtol=0, atol=2e-4, err_msg="logits vs bf16-emulating oracle")
+                np.testing.assert_allclose(val, ev, rtol=0, atol=5e-4, err_msg="value vs bf16-emulating oracle")
+                np.testing.assert_allclose(klog, el[:T], rtol=0, atol=5e-4, err_msg="logits vs bf16-emulating oracle")
+                assert np.mean(np.abs(val - ev) > 2e-5) < 0.02, "more than 2 % of the values off by more than fp32 rounding"
             fin = []
             for t in range(T + 1):
                 with torch.no_grad():
@@ -376,3 +378,39 @@ def test_episode_log_overflow_is_counted():
     big.update(4)
     mb = big.metrics()
     assert mb["episodes"] == m["episodes"] and mb["episodes_dropped"] == 0 and len(mb["episode_log"]) == mb["episodes"]
+
+
+def _mann_whitney_p(x, y):
+    """Two-sided Mann-Whitney U test, normal approximation with tie correction (n = 10 + 10 is large enough for it)."""
+    from scipy import stats
+    return float(stats.mannwhitneyu(x, y, alternative="two-sided").pvalue)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_learning_curve_distribution_matches_the_port(prec):
+    """Learning-curve parity as a DISTRIBUTION (the RNG streams differ by contract): ten seeds of this build at the
+    reference's shape (1 env x 128 steps x 156 updates, deep_rl/ppo.py:62-76) against ten seeds of the CPU port, which is
+    bit-identical to the unmodified reference at the reference's seed (tests/golden/make_port_curves.py).  The last-20-episode
+    mean returns must not be separable: Mann-Whitney p > 0.05 and |difference of means| < 1 pooled standard deviation."""
+    import deep_rl_b200 as drl
+    port = np.load(os.path.join(os.path.dirname(__file__), "golden", "port_curves_10seeds.npz"))
+    want_last, want_first = port["last20"], port["first20"]
+    last, first = [], []
+    for seed in range(1, 11):
+        cfg = drl.PPOConfig(seed=seed, update_precision=prec)
+        tr = drl.PPOTrainer(cfg)
+        eps = []
+        for _ in range(cfg.num_updates()):
+            tr.update()
+            eps += [e[2] for e in tr.metrics()["episode_log"]]
+        first.append(float(np.mean(eps[:20])))
+        last.append(float(np.mean(eps[-20:])))
+    last, first = np.array(last), np.array(first)
+    pooled = float(np.sqrt(0.5 * (last.var(ddof=1) + want_last.var(ddof=1))))
+    p = _mann_whitney_p(last, want_last)
+    print(f"{prec}: last-20 means {np.round(last, 1)} (mean {last.mean():.1f}) vs port {np.round(want_last, 1)} (mean {want_last.mean():.1f}); "
+          f"pooled sd {pooled:.1f}, Mann-Whitney p {p:.3f}")
+    assert p > 0.05, (p, last, want_last)
+    assert abs(last.mean() - want_last.mean()) < pooled, (last.mean(), want_last.mean(), pooled)
+    assert abs(first.mean() - want_first.mean()) < 10.0            # untrained policies: ~22-28 steps per episode on both sides
+    assert last.min() > 2.5 * first.mean()                         # every seed learns
