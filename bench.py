@@ -244,11 +244,13 @@ ROLLOUT_BYTES = {"CartPole-v1": 30, "Acrobot-v1": 38, "MountainCar-v0": 30}
 ENV_STEP_BYTES = {"CartPole-v1": 62 + 32, "Acrobot-v1": 70 + 32, "MountainCar-v0": 62 + 32}             # SURVEY 8d + fp64 state r/w
 
 
-def _timed_updates(tr, nu, steps, flush, dist, dev):
+def _timed_updates(tr, nu, steps, flush, dist, dev, instrument=False):
     """`steps` updates, each bracketed by CUDA events on the launching stream with the L2 flushed before it (outside the
-    events).  Returns (sum of event ms -- max over ranks, per-phase ms, kernel launches)."""
+    events).  instrument=False is the measured configuration (the trainer replays its captured CUDA graph on the tcgen05
+    path); instrument=True additionally brackets every kernel call with CUDA events (eager launches: events cannot be read
+    from inside a replayed graph) and feeds the per-kernel rooflines."""
     import torch
-    tr.timing = True
+    tr.timing = bool(instrument)
     tr.phase_events.clear()
     launches0 = tr.kernel_launches
     evs = []
@@ -355,7 +357,10 @@ def _run_config(name, env_id, envs, T, hidden, steps, warm, rank, world, dev, fl
         tr.update(nu)
     torch.cuda.synchronize()
     evs, l0 = _timed_updates(tr, nu, steps, flush, dist, dev)
-    dev_ms, local_ms, phases, launches = _finish_timed(tr, evs, l0, dist, dev)
+    dev_ms, _, _, launches = _finish_timed(tr, evs, l0, dist, dev)
+    evs, l0 = _timed_updates(tr, nu, max(2, steps // 2), flush, dist, dev, instrument=True)
+    _, local_ms, phases, _ = _finish_timed(tr, evs, l0, dist, dev)
+    inst_steps = max(2, steps // 2)
     m = tr.metrics(with_episode_log=False)
     value = envs * T * world * steps / (dev_ms * 1e-3)
     tc = tr.update_precision == "bf16"
@@ -364,7 +369,8 @@ def _run_config(name, env_id, envs, T, hidden, steps, warm, rank, world, dev, fl
            "dtype": "bf16" if tc else "f32", "episodes_dropped": m["episodes_dropped"],
            "roofline": _grad_roofline(env_id, hidden, cfg.minibatch_size, phases, local_ms, value, world, tc, peaks),
            "rooflines": _hbm_rooflines(env_id, envs, T, cfg.update_epochs, phases, peaks),
-           "phases_ms_per_update": {k: v["total_ms"] / steps for k, v in phases.items()}, "gpu_launches": launches}
+           "phases_ms_per_update": {k: v["total_ms"] / inst_steps for k, v in phases.items()}, "gpu_launches": launches,
+           "cuda_graph": tr._graph is not None}
     if tr.peer is not None:
         tr.peer.close()
     del tr
@@ -462,9 +468,13 @@ def run_b200(args):
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     evs, l0 = _timed_updates(tr, nu, args.steps, flush, dist, dev)
     clocks = sampler.stop() if sampler else None      # last sample while the queued updates are still running
-    dev_ms, local_ms, phases, launches = _finish_timed(tr, evs, l0, dist, dev)
+    dev_ms, _, _, launches = _finish_timed(tr, evs, l0, dist, dev)
     steps_per_update = envs * T * world
     value = steps_per_update * args.steps / (dev_ms * 1e-3)
+    graphed = tr._graph is not None
+    # the same updates once more with CUDA events around every kernel call (eager launches): per-kernel rooflines
+    evs, l0 = _timed_updates(tr, nu, args.steps, flush, dist, dev, instrument=True)
+    inst_ms, local_ms, phases, _ = _finish_timed(tr, evs, l0, dist, dev)
 
     # ---- end to end through the public API: update + host round trip every update ----
     tr.metrics()
@@ -568,7 +578,8 @@ def run_b200(args):
                    "minibatch_size": M, "update_epochs": cfg.update_epochs, "optimizer_steps_per_update": cfg.update_epochs * n_mb,
                    "parallelism": f"env-sharded x{world}" + ("" if world == 1 else (", gradient all-reduce inside the gradient kernel over NVLink peer memory"
                                                                                   if tr_peer else ", NCCL gradient all-reduce per minibatch")), "l2": "flushed between updates (256 MiB memset outside the timed events); "
-                   "every update regenerates its own rollout data"},
+                   "every update regenerates its own rollout data",
+                   "launch": ("one captured CUDA graph per update (26 kernel nodes) + one drl_ctrl_set launch" if graphed else "eager launches")},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / args.steps,
                 "episodes_dropped": dropped,
                 "note": "public API PPOTrainer.update()+metrics() with host syncs and a device->host read of the loss terms, "
@@ -576,6 +587,7 @@ def run_b200(args):
                         "the environments live on the device, so the only per-update host inputs are kernel arguments (no tensor H2D)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu_baseline,
         "phases_ms_per_update": {k: v["total_ms"] / args.steps for k, v in phases.items()},
+        "cuda_graph": graphed, "ms_per_step_eager_instrumented": inst_ms / args.steps,
         "scaling_reference": scaling_ref, "extra_configs": extra, "fp32_path": fp32_path,
     }
     if world > 1:

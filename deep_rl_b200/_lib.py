@@ -41,6 +41,11 @@ class CommT(C.Structure):
                 ("error_flag", C.c_void_p)]
 
 
+class CtrlT(C.Structure):
+    _fields_ = [("env_step", C.c_uint64), ("epoch_ctr", C.c_uint32), ("comm_seq", C.c_uint32), ("adam_step", C.c_int64),
+                ("neg_step_size", C.c_float * 64), ("bc2_sqrt", C.c_float * 64)]
+
+
 class PpoCoefT(C.Structure):
     _fields_ = [("clip_coef", C.c_float), ("ent_coef", C.c_float), ("vf_coef", C.c_float)]
 
@@ -81,6 +86,17 @@ SIGNATURES = {
                                                 f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                                 C.c_double, f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(CommT),
                                                 C.c_void_p]),
+    "drl_ctrl_set": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double,
+                               C.c_void_p]),
+    "drl_rollout_ctl": (C.c_int, [C.POINTER(EnvT), C.POINTER(NetT), f32p, C.c_int32, C.c_void_p, C.POINTER(RolloutBufT),
+                                  C.POINTER(EpLogT), C.c_uint32, C.c_void_p]),
+    "drl_permutation_ctl": (C.c_int, [u32p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "drl_adv_stats_perm_ctl": (C.c_int, [C.POINTER(NetT), f32p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32,
+                                         f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "drl_ppo_minibatch_update_ctl": (C.c_int, [C.POINTER(NetT), f32p, f32p, u32p, C.c_uint32, C.c_uint32, f32p, C.POINTER(PpoCoefT),
+                                               f32p, f32p, f32p, f32p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                               C.c_double, f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(CommT),
+                                               C.c_void_p]),
     "drl_comm_bytes": (C.c_size_t, [C.POINTER(NetT)]),
     "drl_comm_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     "drl_comm_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

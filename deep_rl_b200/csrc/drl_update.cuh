@@ -24,6 +24,9 @@ struct TailArgs {
     unsigned char* peer[DRL_MAX_RANKS];
     uint32_t seq;
     int* error_flag;
+    // graph-replayable launch (drl_ppo_minibatch_update_ctl): Adam scalars and sequence number come from device memory
+    const drl_ctrl_t* ctrl;
+    int ordinal;
 };
 
 // symmetric buffer: two generations (seq & 1) of the folded local gradient, then two generations of arrival flags

@@ -112,7 +112,9 @@ __device__ __forceinline__ uint32_t perm_index(uint32_t i, uint32_t B, uint32_t 
 }
 
 __global__ void __launch_bounds__(256) permutation_kernel(uint32_t* __restrict__ idx, uint32_t B, uint32_t a, uint32_t b,
-                                                           uint64_t seed, uint32_t epoch_ctr, uint32_t rank) {
+                                                           uint64_t seed, uint32_t epoch_ctr, uint32_t rank,
+                                                           const drl_ctrl_t* __restrict__ ctrl) {
+    if (ctrl != nullptr) epoch_ctr += ctrl->epoch_ctr;     // graph-replayable launch: epoch_ctr is the offset inside the update
     const uint4 k0 = philox_seeded(seed, epoch_ctr, rank, 0u, TAG_PERM);
     const uint4 k1 = philox_seeded(seed, epoch_ctr, rank, 1u, TAG_PERM);
     const uint32_t keys[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
@@ -213,7 +215,8 @@ __device__ __forceinline__ uint32_t perm_position(uint32_t s, uint32_t B, uint32
 __global__ void __launch_bounds__(256) adv_stats_perm_kernel(const float* __restrict__ adv, uint32_t B, uint32_t mb_size, uint32_t nmb,
                                                               uint32_t a, uint32_t b, uint64_t seed, uint32_t epoch_ctr, uint32_t rank,
                                                               float* __restrict__ stats_out, double* __restrict__ partials,
-                                                              uint32_t* __restrict__ counter) {
+                                                              uint32_t* __restrict__ counter, const drl_ctrl_t* __restrict__ ctrl) {
+    if (ctrl != nullptr) epoch_ctr += ctrl->epoch_ctr;
     const uint4 k0 = philox_seeded(seed, epoch_ctr, rank, 0u, TAG_PERM);
     const uint4 k1 = philox_seeded(seed, epoch_ctr, rank, 1u, TAG_PERM);
     const uint32_t keys[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
@@ -365,7 +368,8 @@ int drl_explained_variance(const float* values, const float* returns, int64_t n,
     return DRL_OK;
 }
 
-int drl_permutation(uint32_t* idx_out, uint32_t B, uint64_t seed, uint32_t epoch_ctr, uint32_t rank, void* stream) {
+static int permutation_impl(uint32_t* idx_out, uint32_t B, uint64_t seed, uint32_t epoch_ctr, uint32_t rank, void* stream,
+                            const drl_ctrl_t* ctrl) {
     DRL_REQUIRE(idx_out, "drl_permutation: idx_out is NULL");
     DRL_REQUIRE(B > 0 && B <= 0x80000000u, "drl_permutation: B=%u out of range", B);
     DRL_REQUIRE(rank < (1u << 24), "drl_permutation: rank=%u out of range", rank);
@@ -375,9 +379,17 @@ int drl_permutation(uint32_t* idx_out, uint32_t B, uint64_t seed, uint32_t epoch
     long long blocks = ((long long)B + 2047) / 2048;          // ~8 indices per thread amortise the two Philox blocks
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    permutation_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(idx_out, B, a, b, seed, epoch_ctr, rank);
+    permutation_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(idx_out, B, a, b, seed, epoch_ctr, rank, ctrl);
     DRL_LAUNCH_CHECK("permutation_kernel");
     return DRL_OK;
+}
+int drl_permutation(uint32_t* idx_out, uint32_t B, uint64_t seed, uint32_t epoch_ctr, uint32_t rank, void* stream) {
+    return permutation_impl(idx_out, B, seed, epoch_ctr, rank, stream, nullptr);
+}
+int drl_permutation_ctl(uint32_t* idx_out, uint32_t B, uint64_t seed, const drl_ctrl_t* ctrl, uint32_t epoch_off, uint32_t rank,
+                        void* stream) {
+    DRL_REQUIRE(ctrl != nullptr, "drl_permutation_ctl: ctrl is NULL");
+    return permutation_impl(idx_out, B, seed, epoch_off, rank, stream, ctrl);
 }
 
 int drl_adv_stats(const drl_net_t* net, const float* rec, const uint32_t* idx, uint32_t B, uint32_t mb_size,
@@ -402,8 +414,9 @@ int drl_adv_stats(const drl_net_t* net, const float* rec, const uint32_t* idx, u
     return DRL_OK;
 }
 
-int drl_adv_stats_perm(const drl_net_t* net, const float* adv, uint32_t B, uint32_t mb_size, uint64_t seed, uint32_t epoch_ctr,
-                       uint32_t rank, float* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+static int adv_stats_perm_impl(const drl_net_t* net, const float* adv, uint32_t B, uint32_t mb_size, uint64_t seed, uint32_t epoch_ctr,
+                               uint32_t rank, float* stats_out, void* workspace, size_t workspace_bytes, void* stream,
+                               const drl_ctrl_t* ctrl) {
     int rc = check_net(net);
     if (rc != DRL_OK) return rc;
     DRL_REQUIRE(adv && stats_out && workspace, "drl_adv_stats_perm: NULL pointer");
@@ -419,9 +432,18 @@ int drl_adv_stats_perm(const drl_net_t* net, const float* adv, uint32_t B, uint3
     uint32_t blocks = (B + 2047u) / 2048u;
     if (blocks > (uint32_t)STAT_PARTS) blocks = STAT_PARTS;
     adv_stats_perm_kernel<<<blocks, 256, 0, as_stream(stream)>>>(adv, B, mb_size, nmb, k / 2, k - k / 2, seed, epoch_ctr, rank,
-                                                                 stats_out, partials, counter);
+                                                                 stats_out, partials, counter, ctrl);
     DRL_LAUNCH_CHECK("adv_stats_perm_kernel");
     return DRL_OK;
+}
+int drl_adv_stats_perm(const drl_net_t* net, const float* adv, uint32_t B, uint32_t mb_size, uint64_t seed, uint32_t epoch_ctr,
+                       uint32_t rank, float* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return adv_stats_perm_impl(net, adv, B, mb_size, seed, epoch_ctr, rank, stats_out, workspace, workspace_bytes, stream, nullptr);
+}
+int drl_adv_stats_perm_ctl(const drl_net_t* net, const float* adv, uint32_t B, uint32_t mb_size, uint64_t seed, const drl_ctrl_t* ctrl,
+                           uint32_t epoch_off, uint32_t rank, float* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+    DRL_REQUIRE(ctrl != nullptr, "drl_adv_stats_perm_ctl: ctrl is NULL");
+    return adv_stats_perm_impl(net, adv, B, mb_size, seed, epoch_off, rank, stats_out, workspace, workspace_bytes, stream, ctrl);
 }
 
 }  // extern "C"

@@ -14,13 +14,14 @@ namespace drl {
 int check_env(const drl_env_t* env);
 drl_ep_log_t log_or_empty(const drl_ep_log_t* log);
 int launch_rollout_tc(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
-                      const drl_ep_log_t& log, cudaStream_t st);   // rollout_tc.cu
+                      const drl_ep_log_t& log, cudaStream_t st, const drl_ctrl_t* ctrl);   // rollout_tc.cu
 
 constexpr int RO_WARPS = 4;
 
 template <int KIND, int SUB, int TL>
 __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(drl_env_t env, const float* __restrict__ packed, int T,
-                                                                uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log) {
+                                                                uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log, const drl_ctrl_t* __restrict__ ctrl) {
+    if (ctrl != nullptr) step0 = ctrl->env_step;      // graph-replayable launch: the counter lives in device memory
     using S = EnvSpec<KIND>;
     constexpr int O = S::O, A = S::A, OP = S::OP;
     using P = Packed<O, A>;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(drl_env_t env, c
 
 template <int KIND, int SUB, int TL>
 int launch_rollout(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
-                   const drl_ep_log_t& log, cudaStream_t st) {
+                   const drl_ep_log_t& log, cudaStream_t st, const drl_ctrl_t* ctrl) {
     using S = EnvSpec<KIND>;
     constexpr int WS = SUB * OBS_S + H1_S + SUB * OUT_S;
     (void)TL;
@@ -111,7 +112,7 @@ int launch_rollout(const drl_env_t& env, const float* packed, int T, uint64_t st
     DRL_CUDA(cudaFuncSetAttribute(rollout_kernel<KIND, SUB, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int epc = TL * SUB * RO_WARPS;
     const int blocks = (env.num_envs + epc - 1) / epc;
-    rollout_kernel<KIND, SUB, TL><<<blocks, RO_WARPS * 32, smem, st>>>(env, packed, T, step0, buf, log);
+    rollout_kernel<KIND, SUB, TL><<<blocks, RO_WARPS * 32, smem, st>>>(env, packed, T, step0, buf, log, ctrl);
     DRL_LAUNCH_CHECK("rollout_kernel");
     return DRL_OK;
 }
@@ -132,19 +133,19 @@ int pick_envs_per_warp(int N) {
 
 template <int KIND>
 int dispatch_rollout(int epw, const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
-                     const drl_ep_log_t& l, cudaStream_t st) {
-    if (epw == 4) return launch_rollout<KIND, 1, 4>(env, packed, T, step0, buf, l, st);
-    if (epw == 8) return launch_rollout<KIND, 1, 8>(env, packed, T, step0, buf, l, st);
-    if (epw == 16) return launch_rollout<KIND, 2, 8>(env, packed, T, step0, buf, l, st);
-    return launch_rollout<KIND, 4, 8>(env, packed, T, step0, buf, l, st);
+                     const drl_ep_log_t& l, cudaStream_t st, const drl_ctrl_t* ctrl) {
+    if (epw == 4) return launch_rollout<KIND, 1, 4>(env, packed, T, step0, buf, l, st, ctrl);
+    if (epw == 8) return launch_rollout<KIND, 1, 8>(env, packed, T, step0, buf, l, st, ctrl);
+    if (epw == 16) return launch_rollout<KIND, 2, 8>(env, packed, T, step0, buf, l, st, ctrl);
+    return launch_rollout<KIND, 4, 8>(env, packed, T, step0, buf, l, st, ctrl);
 }
 
 }  // namespace drl
 
 using namespace drl;
 
-extern "C" int drl_rollout(const drl_env_t* env, const drl_net_t* net, const float* packed, int32_t T, uint64_t step0,
-                           const drl_rollout_buf_t* buf, const drl_ep_log_t* log, uint32_t flags, void* stream) {
+static int rollout_impl(const drl_env_t* env, const drl_net_t* net, const float* packed, int32_t T, uint64_t step0,
+                        const drl_rollout_buf_t* buf, const drl_ep_log_t* log, uint32_t flags, void* stream, const drl_ctrl_t* ctrl) {
     int rc = check_env(env);
     if (rc != DRL_OK) return rc;
     rc = check_net(net);
@@ -156,9 +157,20 @@ extern "C" int drl_rollout(const drl_env_t* env, const drl_net_t* net, const flo
                 "drl_rollout: net shape does not match env kind %d", env->kind);
     const drl_ep_log_t l = log_or_empty(log);
     cudaStream_t st = as_stream(stream);
-    if (flags & DRL_ROLLOUT_TENSOR_CORES) return launch_rollout_tc(*env, packed, T, step0, *buf, l, st);
+    if (flags & DRL_ROLLOUT_TENSOR_CORES) return launch_rollout_tc(*env, packed, T, step0, *buf, l, st, ctrl);
     const int epw = pick_envs_per_warp(env->num_envs);
-    if (env->kind == DRL_ENV_CARTPOLE) return dispatch_rollout<DRL_ENV_CARTPOLE>(epw, *env, packed, T, step0, *buf, l, st);
-    if (env->kind == DRL_ENV_MOUNTAINCAR) return dispatch_rollout<DRL_ENV_MOUNTAINCAR>(epw, *env, packed, T, step0, *buf, l, st);
-    return dispatch_rollout<DRL_ENV_ACROBOT>(epw, *env, packed, T, step0, *buf, l, st);
+    if (env->kind == DRL_ENV_CARTPOLE) return dispatch_rollout<DRL_ENV_CARTPOLE>(epw, *env, packed, T, step0, *buf, l, st, ctrl);
+    if (env->kind == DRL_ENV_MOUNTAINCAR) return dispatch_rollout<DRL_ENV_MOUNTAINCAR>(epw, *env, packed, T, step0, *buf, l, st, ctrl);
+    return dispatch_rollout<DRL_ENV_ACROBOT>(epw, *env, packed, T, step0, *buf, l, st, ctrl);
+}
+
+extern "C" int drl_rollout(const drl_env_t* env, const drl_net_t* net, const float* packed, int32_t T, uint64_t step0,
+                           const drl_rollout_buf_t* buf, const drl_ep_log_t* log, uint32_t flags, void* stream) {
+    return rollout_impl(env, net, packed, T, step0, buf, log, flags, stream, nullptr);
+}
+
+extern "C" int drl_rollout_ctl(const drl_env_t* env, const drl_net_t* net, const float* packed, int32_t T, const drl_ctrl_t* ctrl,
+                               const drl_rollout_buf_t* buf, const drl_ep_log_t* log, uint32_t flags, void* stream) {
+    DRL_REQUIRE(ctrl != nullptr, "drl_rollout_ctl: ctrl is NULL");
+    return rollout_impl(env, net, packed, T, 0, buf, log, flags, stream, ctrl);
 }

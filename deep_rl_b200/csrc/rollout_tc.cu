@@ -49,7 +49,8 @@ struct RoTcSmem {
 
 template <int KIND, int REP>
 __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env, const float* __restrict__ packed, int T,
-                                                                   uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log) {
+                                                                   uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log, const drl_ctrl_t* __restrict__ ctrl) {
+    if (ctrl != nullptr) step0 = ctrl->env_step;      // graph-replayable launch: the counter lives in device memory
     using SP = EnvSpec<KIND>;
     constexpr int O = SP::O, A = SP::A, OP = SP::OP;
     using P = Packed<O, A>;
@@ -301,20 +302,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
 
 template <int KIND, int REP>
 static int launch_rollout_tc_rep(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
-                                 const drl_ep_log_t& log, cudaStream_t st) {
+                                 const drl_ep_log_t& log, cudaStream_t st, const drl_ctrl_t* ctrl) {
     using SP = EnvSpec<KIND>;
     const int smem = RoTcSmem<SP::O, SP::A>::TOTAL;
     DRL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<KIND, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     constexpr int ROWS = TC_TILE / REP;
     const int blocks = (env.num_envs + ROWS - 1) / ROWS;
-    rollout_tc_kernel<KIND, REP><<<blocks, TC_THREADS, smem, st>>>(env, packed, T, step0, buf, log);
+    rollout_tc_kernel<KIND, REP><<<blocks, TC_THREADS, smem, st>>>(env, packed, T, step0, buf, log, ctrl);
     DRL_LAUNCH_CHECK("rollout_tc_kernel");
     return DRL_OK;
 }
 
 template <int KIND>
 static int launch_rollout_tc_kind(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
-                                  const drl_ep_log_t& log, cudaStream_t st) {
+                                  const drl_ep_log_t& log, cudaStream_t st, const drl_ctrl_t* ctrl) {
     // envs per CTA: 128 when that fills the GPU, otherwise fewer envs per CTA over more CTAs, each env spread over 2 or 4
     // GEMM rows (latency-bound regime)
     const int sms = sm_count();
@@ -323,16 +324,16 @@ static int launch_rollout_tc_kind(const drl_env_t& env, const float* packed, int
     if ((env.num_envs + 63) / 64 < sms && (env.num_envs + 31) / 32 <= sms) rows = 32;
     const char* ov = getenv("DRL_ROLLOUT_ROWS");
     if (ov) { const int v = atoi(ov); if (v == 32 || v == 64 || v == 128) rows = v; }
-    if (rows == 32) return launch_rollout_tc_rep<KIND, 4>(env, packed, T, step0, buf, log, st);
-    if (rows == 64) return launch_rollout_tc_rep<KIND, 2>(env, packed, T, step0, buf, log, st);
-    return launch_rollout_tc_rep<KIND, 1>(env, packed, T, step0, buf, log, st);
+    if (rows == 32) return launch_rollout_tc_rep<KIND, 4>(env, packed, T, step0, buf, log, st, ctrl);
+    if (rows == 64) return launch_rollout_tc_rep<KIND, 2>(env, packed, T, step0, buf, log, st, ctrl);
+    return launch_rollout_tc_rep<KIND, 1>(env, packed, T, step0, buf, log, st, ctrl);
 }
 
 int launch_rollout_tc(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
-                      const drl_ep_log_t& log, cudaStream_t st) {
-    if (env.kind == DRL_ENV_CARTPOLE) return launch_rollout_tc_kind<DRL_ENV_CARTPOLE>(env, packed, T, step0, buf, log, st);
-    if (env.kind == DRL_ENV_MOUNTAINCAR) return launch_rollout_tc_kind<DRL_ENV_MOUNTAINCAR>(env, packed, T, step0, buf, log, st);
-    return launch_rollout_tc_kind<DRL_ENV_ACROBOT>(env, packed, T, step0, buf, log, st);
+                      const drl_ep_log_t& log, cudaStream_t st, const drl_ctrl_t* ctrl) {
+    if (env.kind == DRL_ENV_CARTPOLE) return launch_rollout_tc_kind<DRL_ENV_CARTPOLE>(env, packed, T, step0, buf, log, st, ctrl);
+    if (env.kind == DRL_ENV_MOUNTAINCAR) return launch_rollout_tc_kind<DRL_ENV_MOUNTAINCAR>(env, packed, T, step0, buf, log, st, ctrl);
+    return launch_rollout_tc_kind<DRL_ENV_ACROBOT>(env, packed, T, step0, buf, log, st, ctrl);
 }
 
 }  // namespace drl

@@ -594,6 +594,7 @@ static int run_grad(const drl_net_t* net, const float* packed, const float* rec,
     g.ppad = w.ppad;
     g.dbg = getenv("DRL_TC_DEBUG") ? reinterpret_cast<long long*>((char*)workspace + w.debug) : nullptr;
     g.tail.enabled = 0;
+    g.tail.ctrl = nullptr; g.tail.ordinal = 0;
     if (g_out) { *g_out = g; if (grid_out == nullptr) return DRL_OK; }   // arguments only
     if (flags & DRL_GRAD_TENSOR_CORES) return launch_grad_tc(net, g, P, grad_out, loss_terms_out, st, grid_out);
     if (net->obs_dim == 4) return launch_grad<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, st, grid_out);
@@ -628,7 +629,7 @@ static int minibatch_update_impl(const drl_net_t* net, float* packed, const floa
                                  uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params, float* grad_out,
                                  float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
                                  double max_grad_norm, float* loss_terms_out, float* norm_out, void* workspace, size_t workspace_bytes,
-                                 uint32_t flags, const drl_comm_t* comm, void* stream) {
+                                 uint32_t flags, const drl_comm_t* comm, void* stream, const drl_ctrl_t* ctrl = nullptr, int ordinal = 0) {
     int rc = check_net(net);
     if (rc != DRL_OK) return rc;
     DRL_REQUIRE(params && exp_avg && exp_avg_sq, "drl_ppo_minibatch_update: NULL pointer");
@@ -650,6 +651,7 @@ static int minibatch_update_impl(const drl_net_t* net, float* packed, const floa
         g.tail.ctr = reinterpret_cast<uint32_t*>((char*)workspace + w.counters) + 8;
         g.tail.world = world; g.tail.rank = comm ? comm->rank : 0; g.tail.seq = comm ? comm->seq : 0;
         g.tail.error_flag = comm ? comm->error_flag : nullptr;
+        g.tail.ctrl = ctrl; g.tail.ordinal = ordinal;
         for (int r = 0; r < DRL_MAX_RANKS; ++r)
             g.tail.peer[r] = (comm && r < world) ? reinterpret_cast<unsigned char*>(comm->peer[r]) : nullptr;
         return launch_grad_tc_fused(net, g, st);
@@ -697,6 +699,49 @@ int drl_ppo_minibatch_update_dist(const drl_net_t* net, float* packed, const flo
     return minibatch_update_impl(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, params, grad_out, exp_avg, exp_avg_sq, step,
                                  lr, beta1, beta2, eps, max_grad_norm, loss_terms_out, norm_out, workspace, workspace_bytes, flags,
                                  comm, stream);
+}
+
+int drl_ppo_minibatch_update_ctl(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
+                                 uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params,
+                                 float* grad_out, float* exp_avg, float* exp_avg_sq, const drl_ctrl_t* ctrl, int32_t ordinal,
+                                 double beta1, double beta2, double eps, double max_grad_norm, float* loss_terms_out,
+                                 float* norm_out, void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm,
+                                 void* stream) {
+    DRL_REQUIRE(ctrl != nullptr, "drl_ppo_minibatch_update_ctl: ctrl is NULL");
+    DRL_REQUIRE(ordinal >= 0 && ordinal < DRL_CTRL_MAX_STEPS, "drl_ppo_minibatch_update_ctl: ordinal=%d", ordinal);
+    DRL_REQUIRE(flags & DRL_GRAD_TENSOR_CORES, "drl_ppo_minibatch_update_ctl: tensor-core path only");
+    if (comm != nullptr) {
+        DRL_REQUIRE(comm->world >= 1 && comm->world <= DRL_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world,
+                    "drl_ppo_minibatch_update_ctl: world=%d rank=%d", comm->world, comm->rank);
+        for (int r = 0; r < comm->world; ++r) DRL_REQUIRE(comm->peer[r] != nullptr, "drl_ppo_minibatch_update_ctl: peer[%d] is NULL", r);
+    }
+    // step = 1 / lr = 0 only feed the by-value Adam scalars, which the kernel replaces with ctrl's
+    return minibatch_update_impl(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, params, grad_out, exp_avg, exp_avg_sq, 1,
+                                 0.0, beta1, beta2, eps, max_grad_norm, loss_terms_out, norm_out, workspace, workspace_bytes, flags,
+                                 comm, stream, ctrl, ordinal);
+}
+
+__global__ void ctrl_set_kernel(drl_ctrl_t* dst, drl_ctrl_t v) {
+    if (threadIdx.x == 0) { dst->env_step = v.env_step; dst->epoch_ctr = v.epoch_ctr; dst->comm_seq = v.comm_seq; dst->adam_step = v.adam_step; }
+    if (threadIdx.x < DRL_CTRL_MAX_STEPS) { dst->neg_step_size[threadIdx.x] = v.neg_step_size[threadIdx.x]; dst->bc2_sqrt[threadIdx.x] = v.bc2_sqrt[threadIdx.x]; }
+}
+
+int drl_ctrl_set(drl_ctrl_t* ctrl, uint64_t env_step, uint32_t epoch_ctr, uint32_t comm_seq, int64_t adam_step, int32_t n_steps,
+                 double lr, double beta1, double beta2, void* stream) {
+    DRL_REQUIRE(ctrl != nullptr, "drl_ctrl_set: ctrl is NULL");
+    DRL_REQUIRE(n_steps >= 0 && n_steps <= DRL_CTRL_MAX_STEPS, "drl_ctrl_set: n_steps=%d (max %d)", n_steps, DRL_CTRL_MAX_STEPS);
+    DRL_REQUIRE(adam_step >= 0, "drl_ctrl_set: adam_step=%lld", (long long)adam_step);
+    drl_ctrl_t v;
+    memset(&v, 0, sizeof(v));
+    v.env_step = env_step; v.epoch_ctr = epoch_ctr; v.comm_seq = comm_seq; v.adam_step = adam_step;
+    for (int k = 0; k < n_steps; ++k) {      // the scalars of fill_adam, for optimizer steps adam_step + 1 ... adam_step + n_steps
+        const double step = (double)(adam_step + k + 1);
+        v.neg_step_size[k] = (float)(-(lr / (1.0 - pow(beta1, step))));
+        v.bc2_sqrt[k] = (float)sqrt(1.0 - pow(beta2, step));
+    }
+    ctrl_set_kernel<<<1, DRL_CTRL_MAX_STEPS, 0, as_stream(stream)>>>(ctrl, v);
+    DRL_LAUNCH_CHECK("ctrl_set_kernel");
+    return DRL_OK;
 }
 
 size_t drl_comm_bytes(const drl_net_t* net) {

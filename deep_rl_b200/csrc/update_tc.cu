@@ -605,6 +605,13 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     const TailArgs& tl = g.tail;
     const AdamArgs& ad = tl.a;
     const int PP = ad.P;
+    float neg_step_size = ad.neg_step_size, bc2_sqrt = ad.bc2_sqrt;
+    uint32_t seq = tl.seq;
+    if (tl.ctrl != nullptr) {        // counters of a graph-replayed update live in device memory
+        neg_step_size = tl.ctrl->neg_step_size[tl.ordinal];
+        bc2_sqrt = tl.ctrl->bc2_sqrt[tl.ordinal];
+        seq = tl.ctrl->comm_seq + (uint32_t)tl.ordinal + 1u;
+    }
     const int nparts = gridDim.x;
     float* tred = reinterpret_cast<float*>(sm + S::OFF_H1);              // [8][64] fold scratch (tiles are dead now)
     double* dred = reinterpret_cast<double*>(sm + S::OFF_H1 + 4096);     // [16] warp partials of the squared norm
@@ -626,7 +633,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     const int pl = tid & 63, sl = tid >> 6;        // parameter within a group of 64, slice of the partials (8 slices)
     const bool multi = tl.world > 1;
     const CommLayout cl = comm_layout(PP);
-    const uint32_t gen = tl.seq & 1u;
+    const uint32_t gen = seq & 1u;
     float* xg_local = multi ? reinterpret_cast<float*>(tl.peer[tl.rank] + cl.xgrad[gen]) : nullptr;
     double sq = 0.0;
     for (int p0 = p_lo; p0 < p_hi; p0 += 64) {
@@ -680,12 +687,12 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         grid_barrier(tl.ctr + 1);                 // this rank's whole gradient is in its symmetric buffer
         if (blockIdx.x == 0 && tid < tl.world) {
             __threadfence_system();
-            *reinterpret_cast<volatile uint32_t*>(tl.peer[tid] + cl.flags[gen] + 4 * tl.rank) = tl.seq;
+            *reinterpret_cast<volatile uint32_t*>(tl.peer[tid] + cl.flags[gen] + 4 * tl.rank) = seq;
         }
         if (tid < tl.world) {
             const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(tl.peer[tl.rank] + cl.flags[gen] + 4 * tid);
             const long long t0 = clock64();
-            while (*f < tl.seq) {
+            while (*f < seq) {
                 if (clock64() - t0 > 40000000000ll) {   // ~20 s: a peer is gone (start-up skew between ranks can reach seconds)
                     if (tl.error_flag) { *reinterpret_cast<volatile int*>(tl.error_flag) = 1; __threadfence(); }
                     break;
@@ -746,8 +753,8 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         else { m = ad.m[p]; v = ad.v[p]; wgt = ad.params[p]; }
         m = m + ad.om_beta1 * (gsc - m);
         v = v * ad.beta2 + (ad.om_beta2 * gsc) * gsc;
-        const float denom = sqrtf(v) / ad.bc2_sqrt + ad.eps;
-        wgt = wgt + (ad.neg_step_size * m) / denom;
+        const float denom = sqrtf(v) / bc2_sqrt + ad.eps;
+        wgt = wgt + (neg_step_size * m) / denom;
         ad.m[p] = m; ad.v[p] = v; ad.params[p] = wgt;
         if (ad.packed != nullptr) packed_store<O, A>(ad.packed, p, wgt);
     }

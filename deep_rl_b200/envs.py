@@ -53,19 +53,31 @@ class EpisodeLog:
 
     def drain_arrays(self):
         """D2H read + clear without Python-object conversion: (count, sum_ret, sum_len, {"step","env","ret","len"} numpy views
-        of pinned host buffers, unsorted, valid until the next drain).  Two synchronisations: the header, then the entries."""
-        n, sum_ret, sum_len = self.read_header()
-        k = min(n, self.cap)
+        of pinned host buffers, unsorted, valid until the next drain).  ONE synchronisation in the steady state: the header
+        and a speculative prefix of the entries (1.25 x the previous count) are copied together; only when more episodes
+        finished than guessed does a second copy + synchronisation fetch the rest."""
         if not hasattr(self, "_host"):
             self._host = {"step": torch.zeros(self.cap, dtype=torch.int64).pin_memory(), "env": torch.zeros(self.cap, dtype=torch.int32).pin_memory(),
                           "ret": torch.zeros(self.cap, dtype=torch.float32).pin_memory(), "len": torch.zeros(self.cap, dtype=torch.int32).pin_memory()}
-        if k:
-            for name, src in (("step", self.step), ("env", self.env), ("ret", self.ret), ("len", self.len)):
-                self._host[name][:k].copy_(src[:k], non_blocking=True)
+            self._guess = 0
+        srcs = (("step", self.step), ("env", self.env), ("ret", self.ret), ("len", self.len))
+        g = min(self.cap, self._guess)
+        self._hdr_host.copy_(self._hdr, non_blocking=True)
+        if g:
+            for name, src in srcs:
+                self._host[name][:g].copy_(src[:g], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n = int(self._hdr_host[0:4].view(torch.int32).item())
+        s = self._hdr_host[8:24].view(torch.float64).tolist()
+        k = min(n, self.cap)
+        if k > g:
+            for name, src in srcs:
+                self._host[name][g:k].copy_(src[g:k], non_blocking=True)
             torch.cuda.current_stream().synchronize()
         self.clear()
-        self.last_d2h_bytes = 24 + 20 * k
-        return n, sum_ret, sum_len, {name: buf[:k].numpy() for name, buf in self._host.items()}
+        self.last_d2h_bytes = 24 + 20 * max(k, g)
+        self._guess = k + k // 4 + 64
+        return n, s[0], s[1], {name: buf[:k].numpy() for name, buf in self._host.items()}
 
     def drain(self, with_entries: bool = True):
         """D2H read + clear.  Returns (count, sum_ret, sum_len, entries sorted by (step, env))."""

@@ -66,6 +66,8 @@ class PPOConfig:
     update_precision: str = "auto"   # "bf16": tcgen05 tensor-core update (bf16 operands, fp32 accumulate); "fp32": CUDA-core
                                      # update; "auto": bf16 from 2048 envs per rank (minibatches of >= 64k samples), else fp32
     debug_logits: bool = False       # record the logits every action was sampled from ([T][N][A] plane, parity tests)
+    cuda_graph: bool = True          # tcgen05 path: capture the launches of one update in a CUDA graph (counters live in a
+                                     # device-resident drl_ctrl_t) and replay it; results are bit-identical to the eager path
 
     def resolved_update_precision(self) -> str:
         if self.update_precision == "auto":
@@ -187,6 +189,14 @@ class PPOTrainer:
             self.peer = _dist.PeerComm(self.net, self.rank, self.world, dev)
         self.timing = False        # record CUDA events around each phase (bench.py)
         self.phase_events: Dict[str, list] = {}
+        # graph-replayable update: device-resident counters + one captured graph (tcgen05 fused step only)
+        self.ctrl = torch.zeros(C.sizeof(_lib.CtrlT), dtype=u8, device=dev)
+        self._graph = None
+        self._graph_launches = 0
+        self._graph_warm = 0
+        n_opt = cfg.update_epochs * self.n_mb
+        self.graph_ok = bool(cfg.cuda_graph and self.grad_flags == 1 and self.n_mb <= 8 and n_opt <= 64 and not self._merge_stats
+                             and (self.world == 1 or self.peer is not None))
 
     def phase_ms(self) -> Dict[str, Dict[str, float]]:
         """Per-phase device time from the recorded events: {phase: {calls, total_ms, mean_ms}} (synchronises)."""
@@ -203,13 +213,18 @@ class PPOTrainer:
             return self.cfg.learning_rate
         return (1.0 - update / num_updates) * self.cfg.learning_rate      # ppo.py:107-108
 
-    def rollout(self) -> None:
+    def rollout(self, ctl: bool = False) -> None:
         """ppo.py:110-141 for all envs: one kernel launch."""
         cfg = self.cfg
         with _Phase(self, "rollout"):
-            _lib.check(self.L.drl_rollout(C.byref(self.env.struct), C.byref(self.net), self.agent.packed.data_ptr(),
-                                          cfg.num_steps, self.env.step_count, C.byref(self.buf),
-                                          C.byref(self.env.log.struct), self.rollout_flags, _lib.stream_ptr()))
+            if ctl:
+                _lib.check(self.L.drl_rollout_ctl(C.byref(self.env.struct), C.byref(self.net), self.agent.packed.data_ptr(),
+                                                  cfg.num_steps, self.ctrl.data_ptr(), C.byref(self.buf),
+                                                  C.byref(self.env.log.struct), self.rollout_flags, _lib.stream_ptr()))
+            else:
+                _lib.check(self.L.drl_rollout(C.byref(self.env.struct), C.byref(self.net), self.agent.packed.data_ptr(),
+                                              cfg.num_steps, self.env.step_count, C.byref(self.buf),
+                                              C.byref(self.env.log.struct), self.rollout_flags, _lib.stream_ptr()))
         self.env.step_count += cfg.num_steps
         self.global_step += cfg.num_steps * cfg.num_envs * self.world
         self.kernel_launches += 1
@@ -226,7 +241,7 @@ class PPOTrainer:
     def _side(self):
         return torch.cuda.stream(self.side) if self.side is not None else contextlib.nullcontext()
 
-    def schedule_permutations(self) -> None:
+    def schedule_permutations(self, ctl: bool = False) -> None:
         """ppo.py:155 for every epoch of the coming update.  The keyed permutation depends on counters only, so with
         `overlap_streams` it runs on the side stream while the rollout kernel runs on the main one."""
         cfg = self.cfg
@@ -237,11 +252,15 @@ class PPOTrainer:
             for epoch in range(cfg.update_epochs):
                 epoch_ctr = self.update_idx * cfg.update_epochs + epoch
                 with _Phase(self, "permutation"):
-                    _lib.check(self.L.drl_permutation(self.idx[epoch].data_ptr(), cfg.batch_size, cfg.seed, epoch_ctr, self.rank, st))
+                    if ctl:
+                        _lib.check(self.L.drl_permutation_ctl(self.idx[epoch].data_ptr(), cfg.batch_size, cfg.seed, self.ctrl.data_ptr(),
+                                                              epoch, self.rank, st))
+                    else:
+                        _lib.check(self.L.drl_permutation(self.idx[epoch].data_ptr(), cfg.batch_size, cfg.seed, epoch_ctr, self.rank, st))
         self.kernel_launches += cfg.update_epochs
         self._perms_scheduled = True
 
-    def schedule_adv_stats(self) -> None:
+    def schedule_adv_stats(self, ctl: bool = False) -> None:
         """ppo.py:169 statistics of every (epoch, minibatch): needs the advantages, i.e. runs after GAE; epoch e + 1's pass
         overlaps epoch e's minibatch steps on the side stream."""
         cfg = self.cfg
@@ -255,7 +274,11 @@ class PPOTrainer:
             for epoch in range(cfg.update_epochs):
                 epoch_ctr = self.update_idx * cfg.update_epochs + epoch
                 with _Phase(self, "adv_stats"):
-                    if self.n_mb <= 8:   # no gather: natural-order pass over the advantage plane + inverse permutation
+                    if ctl:
+                        _lib.check(self.L.drl_adv_stats_perm_ctl(net, self.advantages.data_ptr(), B, M, cfg.seed, self.ctrl.data_ptr(), epoch,
+                                                                 self.rank, self.adv_stats[epoch].data_ptr(), self.workspace.data_ptr(),
+                                                                 self.ws_bytes, st))
+                    elif self.n_mb <= 8:   # no gather: natural-order pass over the advantage plane + inverse permutation
                         _lib.check(self.L.drl_adv_stats_perm(net, self.advantages.data_ptr(), B, M, cfg.seed, epoch_ctr, self.rank,
                                                              self.adv_stats[epoch].data_ptr(), self.workspace.data_ptr(),
                                                              self.ws_bytes, st))
@@ -272,7 +295,7 @@ class PPOTrainer:
                         ev.record()
         self.kernel_launches += cfg.update_epochs
 
-    def optimize(self, lr: float) -> None:
+    def optimize(self, lr: float, ctl: bool = False) -> None:
         """ppo.py:154-192."""
         cfg = self.cfg
         B, M = cfg.batch_size, cfg.minibatch_size
@@ -281,9 +304,9 @@ class PPOTrainer:
             raise _lib.DrlError("world > 1 needs an initialised torch.distributed process group for the gradient all-reduce "
                                 "(deep_rl_b200.dist.init_from_env); without it the gradient would only be scaled by 1/world")
         if not self._perms_scheduled:
-            self.schedule_permutations()
+            self.schedule_permutations(ctl)
         self._perms_scheduled = False
-        self.schedule_adv_stats()
+        self.schedule_adv_stats(ctl)
         st = _lib.stream_ptr()
         for epoch in range(cfg.update_epochs):
             if self.side is not None:
@@ -294,6 +317,20 @@ class PPOTrainer:
                 start = k * M
                 count = min(M, B - start)
                 row = epoch * self.n_mb + k
+                if ctl:     # counters from the device control block: the launch is identical from update to update
+                    self.adam_step += 1
+                    if self.peer is not None:
+                        self.peer.next()
+                    with _Phase(self, "minibatch_grad"):
+                        _lib.check(self.L.drl_ppo_minibatch_update_ctl(
+                            net, self.agent.packed.data_ptr(), self.records.data_ptr(), idx_ptr, start, count,
+                            stats_ptr + 8 * k, C.byref(self.coef), self.agent.flat_params.data_ptr(),
+                            self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.ctrl.data_ptr(), row,
+                            0.9, 0.999, 1e-5, cfg.max_grad_norm, self.loss_terms.data_ptr() + 32 * row,
+                            self.grad_norm.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, self.grad_flags,
+                            C.byref(self.peer.struct) if self.peer is not None else None, st))
+                    self.kernel_launches += 1
+                    continue
                 if self.peer is not None:
                     self.adam_step += 1
                     with _Phase(self, "minibatch_grad"):    # gradient + fold + NVLink all-reduce + clip + Adam: one launch
@@ -333,16 +370,64 @@ class PPOTrainer:
                                                     self.agent.packed.data_ptr(), self.grad_norm.data_ptr(), st))
                 self.kernel_launches += 3
 
+    def _issue_update(self, lr: float, ctl: bool) -> None:
+        self.schedule_permutations(ctl)
+        self.rollout(ctl)
+        self.compute_gae()
+        self.optimize(lr, ctl)
+
     def update(self, num_updates: Optional[int] = None) -> None:
-        """One full update (rollout + GAE + epochs), asynchronous: no host synchronisation."""
+        """One full update (rollout + GAE + epochs), asynchronous: no host synchronisation.  On the tcgen05 path the launches
+        are captured once in a CUDA graph (third update onwards) and replayed; per update the host then issues one tiny
+        drl_ctrl_set launch (step / epoch / Adam counters, learning rate) and one graph launch."""
         nu = num_updates if num_updates is not None else max(1, self.cfg.num_updates(self.world))
         lr = self.learning_rate(self.update_idx, nu)
-        self.schedule_permutations()
-        self.rollout()
-        self.compute_gae()
-        self.optimize(lr)
+        use_ctl = self.graph_ok and not self.timing
+        if not use_ctl:
+            self._issue_update(lr, False)
+        else:
+            cfg = self.cfg
+            n_opt = cfg.update_epochs * self.n_mb
+            _lib.check(self.L.drl_ctrl_set(self.ctrl.data_ptr(), self.env.step_count, self.update_idx * cfg.update_epochs,
+                                           self.peer.seq if self.peer is not None else 0, self.adam_step, n_opt, lr, 0.9, 0.999,
+                                           _lib.stream_ptr()))
+            if self._graph is None and self._graph_warm >= 2:
+                self._capture_graph(lr)
+            if self._graph is not None:
+                self._graph.replay()
+                self._advance_host_counters(n_opt)
+                self.kernel_launches += self._graph_launches
+            else:
+                self._graph_warm += 1
+                self._issue_update(lr, True)
+            self.kernel_launches += 1       # drl_ctrl_set
         self.update_idx += 1
         self.agent.mark_packed_current()
+
+    def _advance_host_counters(self, n_opt: int) -> None:
+        """Host mirrors of the counters the replayed kernels read from the control block."""
+        cfg = self.cfg
+        self.env.step_count += cfg.num_steps
+        self.global_step += cfg.num_steps * cfg.num_envs * self.world
+        self.adam_step += n_opt
+        if self.peer is not None:
+            self.peer.seq += n_opt
+
+    def _capture_graph(self, lr: float) -> None:
+        """Stream-capture one update issued through the *_ctl entry points.  Nothing executes during capture, so the host
+        counters are restored afterwards; the side-stream fork / join (permutations, statistics) becomes part of the graph."""
+        snap = (self.env.step_count, self.global_step, self.adam_step, self.kernel_launches, self.peer.seq if self.peer is not None else 0,
+                self._perms_scheduled)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._issue_update(lr, True)
+        self._graph_launches = self.kernel_launches - snap[3]
+        self.env.step_count, self.global_step, self.adam_step, self.kernel_launches = snap[0], snap[1], snap[2], snap[3]
+        if self.peer is not None:
+            self.peer.seq = snap[4]
+        self._perms_scheduled = False
+        self._graph = g
 
     def metrics(self, with_episode_log: bool = True) -> Dict[str, float]:
         """Device->host read of the last update's loss terms, gradient norm and finished-episode statistics

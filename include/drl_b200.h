@@ -85,6 +85,20 @@ typedef struct {
     float vf_coef;    /* ppo.py:74 */
 } drl_ppo_coef_t;
 
+/* Device-resident counters of one trainer (caller-owned device memory, sizeof(drl_ctrl_t) bytes).  The *_ctl entry points
+ * read their step / epoch / optimizer-step numbers from it instead of from by-value arguments, so that the launches of a
+ * whole update can be captured ONCE in a CUDA graph and replayed: only drl_ctrl_set (outside the graph, one tiny launch whose
+ * kernel parameters carry the new values) runs per update. */
+#define DRL_CTRL_MAX_STEPS 64
+typedef struct {
+    uint64_t env_step;    /* Philox step index of the first rollout step (= step0 of drl_rollout) */
+    uint32_t epoch_ctr;   /* permutation counter of the update's first epoch */
+    uint32_t comm_seq;    /* sequence number of the last fused multi-GPU minibatch step before this update */
+    int64_t  adam_step;   /* optimizer steps taken before this update */
+    float    neg_step_size[DRL_CTRL_MAX_STEPS];   /* -lr / (1 - beta1^k) for the update's k-th optimizer step */
+    float    bc2_sqrt[DRL_CTRL_MAX_STEPS];        /* sqrt(1 - beta2^k) */
+} drl_ctrl_t;
+
 int         drl_abi_version(void);
 const char* drl_last_error(void);
 
@@ -122,6 +136,18 @@ int drl_sample(const float* logits /*[n][A]*/, int64_t n, int32_t num_actions, u
 #define DRL_ROLLOUT_TENSOR_CORES 1u   /* flags: hidden layers on tcgen05 (bf16 operands, fp32 accumulate), 128 envs per CTA */
 int drl_rollout(const drl_env_t* env, const drl_net_t* net, const float* packed, int32_t T, uint64_t step0,
                 const drl_rollout_buf_t* buf, const drl_ep_log_t* log, uint32_t flags, void* stream);
+
+/* ---- graph-replayable variants: same kernels, counters read from *ctrl (device memory) ----
+ * drl_ctrl_set computes the Adam scalars of the coming n_steps optimizer steps (same fp64 host arithmetic as drl_clip_adam) and
+ * writes the whole block with one kernel launch. */
+int drl_ctrl_set(drl_ctrl_t* ctrl, uint64_t env_step, uint32_t epoch_ctr, uint32_t comm_seq, int64_t adam_step, int32_t n_steps,
+                 double lr, double beta1, double beta2, void* stream);
+int drl_rollout_ctl(const drl_env_t* env, const drl_net_t* net, const float* packed, int32_t T, const drl_ctrl_t* ctrl,
+                    const drl_rollout_buf_t* buf, const drl_ep_log_t* log, uint32_t flags, void* stream);
+int drl_permutation_ctl(uint32_t* idx_out, uint32_t B, uint64_t seed, const drl_ctrl_t* ctrl, uint32_t epoch_off, uint32_t rank,
+                        void* stream);                       /* epoch counter = ctrl->epoch_ctr + epoch_off */
+int drl_adv_stats_perm_ctl(const drl_net_t* net, const float* adv, uint32_t B, uint32_t mb_size, uint64_t seed, const drl_ctrl_t* ctrl,
+                           uint32_t epoch_off, uint32_t rank, float* stats_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- GAE + returns, ppo.py:144-151; optionally packs per-sample records for the update ----
  * adv_out/ret_out are [T+1][N] (row T = 0 / val[T], as the reference leaves them).
@@ -191,6 +217,16 @@ int drl_ppo_minibatch_update_dist(const drl_net_t* net, float* packed, const flo
                                   float* grad_out, float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1,
                                   double beta2, double eps, double max_grad_norm, float* loss_terms_out, float* norm_out,
                                   void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm, void* stream);
+
+/* Graph-replayable form of the two calls above (tensor-core path): `ordinal` = index of this optimizer step inside the update
+ * (Adam scalars ctrl->neg_step_size[ordinal], ctrl->bc2_sqrt[ordinal]; sequence number ctrl->comm_seq + ordinal + 1);
+ * comm NULL = single GPU, otherwise its `seq` field is ignored. */
+int drl_ppo_minibatch_update_ctl(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
+                                 uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params,
+                                 float* grad_out, float* exp_avg, float* exp_avg_sq, const drl_ctrl_t* ctrl, int32_t ordinal,
+                                 double beta1, double beta2, double eps, double max_grad_norm, float* loss_terms_out,
+                                 float* norm_out, void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm,
+                                 void* stream);
 
 /* ---- clip_grad_norm_ + Adam, ppo.py:191-192 (after the gradient all-reduce) ----
  * grad is multiplied by grad_scale (1/world) first; `step` is the 1-based Adam step of this call.

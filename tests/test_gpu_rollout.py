@@ -414,3 +414,43 @@ def test_learning_curve_distribution_matches_the_port(prec):
     assert abs(last.mean() - want_last.mean()) < pooled, (last.mean(), want_last.mean(), pooled)
     assert abs(first.mean() - want_first.mean()) < 10.0            # untrained policies: ~22-28 steps per episode on both sides
     assert last.min() > 2.5 * first.mean()                         # every seed learns
+
+
+@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 256, 16), ("Acrobot-v1", 96, 24)])
+def test_cuda_graph_update_is_bit_identical_to_eager(env_id, N, T):
+    """The graph-replayed update (device-resident counters, drl_*_ctl entry points) must not change a single bit against the
+    eager path with by-value counters: parameters, Adam moments, loss terms, env state, rollout buffers, episode log."""
+    import deep_rl_b200 as drl
+    out = []
+    for graph in (False, True):
+        cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=6, total_timesteps=N * T * 12, update_precision="bf16",
+                            cuda_graph=graph)
+        tr = drl.PPOTrainer(cfg)
+        logs = []
+        for u in range(7):
+            tr.update(12)
+            if u in (1, 4, 6):
+                m = tr.metrics()
+                logs.append((m["episodes"], m["loss"], m["grad_norm"], m["episode_log"]))
+        torch.cuda.synchronize()
+        assert (tr._graph is not None) == graph
+        out.append((tr.agent.flat_params.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone(), tr.loss_terms.clone(), tr.env.state.clone(),
+                    tr.observations.clone(), tr.actions.clone(), tr.advantages.clone(), logs, tr.env.step_count, tr.adam_step,
+                    tr.global_step))
+    for a, b in zip(out[0], out[1]):
+        if isinstance(a, torch.Tensor):
+            assert torch.equal(a, b)
+        else:
+            assert a == b
+    # a checkpoint taken from the graph-replaying trainer resumes bit-identically in an eager one
+    g = drl.PPOTrainer(drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=6, total_timesteps=N * T * 12, update_precision="bf16"))
+    for _ in range(4):
+        g.update(12)
+    sd = g.state_dict()
+    g.update(12)
+    e = drl.PPOTrainer(drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=6, total_timesteps=N * T * 12, update_precision="bf16",
+                                     cuda_graph=False))
+    e.load_state_dict(sd)
+    e.update(12)
+    torch.cuda.synchronize()
+    assert torch.equal(g.agent.flat_params, e.agent.flat_params) and torch.equal(g.env.state, e.env.state)
