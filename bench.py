@@ -482,14 +482,22 @@ def run_b200(args):
     torch.cuda.synchronize()
     d2h, dropped = 0, 0
     t0 = time.perf_counter()
+    pending = None
     for _ in range(args.steps):
         tr.update(nu)
-        # D2H every update, like the reference's prints: loss terms + grad norm (36 B), episode count + sums (24 B) and the
-        # (step, env, return, length) record of every finished episode (20 B each)
-        m = tr.metrics(with_episode_log="arrays")
-        d2h += 36 + tr.env.log.last_d2h_bytes
-        dropped += m["episodes_dropped"]
-        _ = (m["mean_return"], m["loss"], len(m["episode_log"]["ret"]))
+        # D2H every update, like the reference's prints: loss terms + grad norm (36 B), episode count + sums (32 B) and the
+        # (step, env, return, length) record of every finished episode (24 B each).  The read of update k is enqueued right
+        # behind it and consumed on the host while update k+1 runs (metrics_async); every record is read inside this region.
+        h = tr.metrics_async()
+        d2h += h.d2h_bytes
+        if pending is not None:
+            m = pending.result()
+            dropped += m["episodes_dropped"]
+            _ = (m["mean_return"], m["loss"], len(m["episode_log"]["ret"]))
+        pending = h
+    m = pending.result()
+    dropped += m["episodes_dropped"]
+    _ = (m["mean_return"], m["loss"], len(m["episode_log"]["ret"]))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_s = dist.all_reduce_max(e2e_s, dev)
@@ -582,8 +590,9 @@ def run_b200(args):
                    "launch": ("one captured CUDA graph per update (26 kernel nodes) + one drl_ctrl_set launch" if graphed else "eager launches")},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h / args.steps,
                 "episodes_dropped": dropped,
-                "note": "public API PPOTrainer.update()+metrics() with host syncs and a device->host read of the loss terms, "
-                        "gradient norm, episode statistics and the per-episode records (what the reference prints) every update; "
+                "note": "public API PPOTrainer.update() + metrics_async().result(): every update is followed by a device->host read of "
+                        "its loss terms, gradient norm, episode statistics and per-episode records (what the reference prints) into "
+                        "pinned memory; the host consumes update k's read while update k+1 runs; wall clock around the whole loop; "
                         "the environments live on the device, so the only per-update host inputs are kernel arguments (no tensor H2D)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu_baseline,
         "phases_ms_per_update": {k: v["total_ms"] / args.steps for k, v in phases.items()},

@@ -23,8 +23,8 @@ class EnvT(C.Structure):
 
 
 class EpLogT(C.Structure):
-    _fields_ = [("count", C.c_void_p), ("sum_ret", C.c_void_p), ("sum_len", C.c_void_p), ("log_ret", C.c_void_p),
-                ("log_len", C.c_void_p), ("log_env", C.c_void_p), ("log_step", C.c_void_p), ("cap", C.c_uint32)]
+    _fields_ = [("count", C.c_void_p), ("sum_ret", C.c_void_p), ("sum_len", C.c_void_p), ("entries", C.c_void_p),
+                ("cap", C.c_uint32)]
 
 
 class NetT(C.Structure):

@@ -176,11 +176,10 @@ __device__ __forceinline__ bool env_step(EnvLane& e, int action, float& reward, 
             base = __shfl_sync(active, base, leader);
             if (done) {
                 const uint32_t slot = base + (uint32_t)__popc(dmask & ((1u << lane) - 1u));
-                if (slot < log.cap && log.log_ret) {
-                    log.log_ret[slot] = e.ep_ret;
-                    log.log_len[slot] = e.ep_len;
-                    log.log_env[slot] = gid;
-                    log.log_step[slot] = step;
+                if (slot < log.cap && log.entries) {      // one 24-byte record: a 16-byte and an 8-byte store
+                    drl_ep_entry_t en;
+                    en.step = step; en.env = gid; en.ret = e.ep_ret; en.len = e.ep_len; en.pad = 0u;
+                    log.entries[slot] = en;
                 }
             }
         }

@@ -13,6 +13,7 @@ import ctypes as C
 from types import SimpleNamespace
 from typing import Optional
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -21,74 +22,123 @@ ENV_KINDS = {"CartPole-v1": 0, "Acrobot-v1": 1, "MountainCar-v0": 2}
 MAX_EPISODE_STEPS = {"CartPole-v1": 500, "Acrobot-v1": 500, "MountainCar-v0": 200}      # TimeLimit of the gym registrations
 
 
+ENTRY_DTYPE = np.dtype([("step", "<u8"), ("env", "<u4"), ("ret", "<f4"), ("len", "<i4"), ("pad", "<u4")])     # drl_ep_entry_t
+HDR_BYTES = 32        # u32 count | pad | f64 sum_ret | f64 sum_len | pad
+
+
+class LogRead:
+    """A device->host read of the episode log in flight (EpisodeLog.read_async): result() waits for it."""
+
+    def __init__(self, log: "EpisodeLog", host: torch.Tensor, guess: int, event: torch.cuda.Event):
+        self.log, self.host, self.guess, self.event = log, host, guess, event
+
+    def result(self):
+        """(count, sum_ret, sum_len, entries as a numpy structured array view [step, env, ret, len], entries lost).  Entries
+        beyond the speculative prefix were already overwritten when this is called and count as lost (none in the steady
+        state: the prefix is twice the previous count)."""
+        self.event.synchronize()
+        raw = self.host.numpy()
+        n = int(raw[0:4].view(np.uint32)[0])
+        sums = raw[8:24].view(np.float64)
+        k = min(n, self.guess)
+        entries = raw[HDR_BYTES:HDR_BYTES + 24 * k].view(ENTRY_DTYPE)
+        self.log._guess = min(self.log.cap, 2 * n + 1024)
+        return n, float(sums[0]), float(sums[1]), entries, n - k
+
+
 class EpisodeLog:
-    """Finished-episode log written by the kernels (drl_ep_log_t)."""
+    """Finished-episode log written by the kernels (drl_ep_log_t): one device buffer = 32-byte header (count, sums) followed by
+    `cap` 24-byte records, so that header + a prefix of the records travel to the host in ONE copy."""
 
     def __init__(self, cap: int, device):
         self.cap = int(cap)
-        # count (int32 @0) and the two float64 sums (@8, @16) share one 24-byte buffer: one fill clears them,
-        # one 24-byte device->host copy reads them.
-        self._hdr = torch.zeros(24, dtype=torch.uint8, device=device)
-        self.count = self._hdr[0:4].view(torch.int32)
-        self.sums = self._hdr[8:24].view(torch.float64)      # sum_ret, sum_len
-        self._hdr_host = torch.zeros(24, dtype=torch.uint8).pin_memory()
-        self.ret = torch.zeros(self.cap, dtype=torch.float32, device=device)
-        self.len = torch.zeros(self.cap, dtype=torch.int32, device=device)
-        self.env = torch.zeros(self.cap, dtype=torch.int32, device=device)
-        self.step = torch.zeros(self.cap, dtype=torch.int64, device=device)
-        self.struct = _lib.EpLogT(self.count.data_ptr(), self.sums.data_ptr(), self.sums.data_ptr() + 8,
-                                  self.ret.data_ptr(), self.len.data_ptr(), self.env.data_ptr(), self.step.data_ptr(),
-                                  self.cap)
+        self.buf = torch.zeros(HDR_BYTES + 24 * self.cap, dtype=torch.uint8, device=device)
+        self._hdr = self.buf[:HDR_BYTES]
+        self.count = self.buf[0:4].view(torch.int32)
+        self.sums = self.buf[8:24].view(torch.float64)      # sum_ret, sum_len
+        self._words = self.buf[HDR_BYTES:].view(torch.int32).view(self.cap, 6)      # step lo, step hi, env, ret bits, len, pad
+        self.struct = _lib.EpLogT(self.buf.data_ptr(), self.buf.data_ptr() + 8, self.buf.data_ptr() + 16,
+                                  self.buf.data_ptr() + HDR_BYTES, self.cap)
+        self._host = [torch.zeros(HDR_BYTES + 24 * self.cap, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._flip = 0
+        self._guess = min(self.cap, 1024)
+        self.last_d2h_bytes = 0
 
-    def read_header(self):
-        """(count, sum_ret, sum_len): one 24-byte D2H copy (synchronises the current stream)."""
-        self._hdr_host.copy_(self._hdr, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        n = int(self._hdr_host[0:4].view(torch.int32).item())
-        s = self._hdr_host[8:24].view(torch.float64).tolist()
-        return n, s[0], s[1]
+    # typed views of the record fields (tests, single-env gym API)
+    @property
+    def ret(self) -> torch.Tensor:
+        return self._words[:, 3].contiguous().view(torch.float32)
+
+    @property
+    def len(self) -> torch.Tensor:
+        return self._words[:, 4]
+
+    @property
+    def env(self) -> torch.Tensor:
+        return self._words[:, 2]
+
+    @property
+    def step(self) -> torch.Tensor:
+        return self._words[:, 0:2].contiguous().view(torch.int64).reshape(-1)
 
     def clear(self):
         self._hdr.zero_()
 
+    def read_async(self) -> LogRead:
+        """Enqueue (current stream) ONE copy of header + a speculative prefix of the records into pinned memory, then the
+        clear of the header; returns the handle whose result() waits for the copy.  Two pinned buffers alternate, so the
+        read of update k may be consumed while update k+1 is already running."""
+        host = self._host[self._flip]
+        self._flip ^= 1
+        g = self._guess
+        nbytes = HDR_BYTES + 24 * g
+        host[:nbytes].copy_(self.buf[:nbytes], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.clear()
+        self.last_d2h_bytes = nbytes
+        return LogRead(self, host, g, ev)
+
     def drain_arrays(self):
-        """D2H read + clear without Python-object conversion: (count, sum_ret, sum_len, {"step","env","ret","len"} numpy views
-        of pinned host buffers, unsorted, valid until the next drain).  ONE synchronisation in the steady state: the header
-        and a speculative prefix of the entries (1.25 x the previous count) are copied together; only when more episodes
-        finished than guessed does a second copy + synchronisation fetch the rest."""
-        if not hasattr(self, "_host"):
-            self._host = {"step": torch.zeros(self.cap, dtype=torch.int64).pin_memory(), "env": torch.zeros(self.cap, dtype=torch.int32).pin_memory(),
-                          "ret": torch.zeros(self.cap, dtype=torch.float32).pin_memory(), "len": torch.zeros(self.cap, dtype=torch.int32).pin_memory()}
-            self._guess = 0
-        srcs = (("step", self.step), ("env", self.env), ("ret", self.ret), ("len", self.len))
-        g = min(self.cap, self._guess)
-        self._hdr_host.copy_(self._hdr, non_blocking=True)
-        if g:
-            for name, src in srcs:
-                self._host[name][:g].copy_(src[:g], non_blocking=True)
+        """Synchronous D2H read + clear: (count, sum_ret, sum_len, {"step","env","ret","len"} numpy views of a pinned host
+        buffer, unsorted, valid until the next-but-one read).  One copy + one synchronisation in the steady state; only when
+        more episodes finished than the speculative prefix holds does a second copy fetch the rest (before the clear)."""
+        host = self._host[self._flip]
+        self._flip ^= 1
+        g = self._guess
+        host[:HDR_BYTES + 24 * g].copy_(self.buf[:HDR_BYTES + 24 * g], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        n = int(self._hdr_host[0:4].view(torch.int32).item())
-        s = self._hdr_host[8:24].view(torch.float64).tolist()
+        raw = host.numpy()
+        n = int(raw[0:4].view(np.uint32)[0])
+        sums = raw[8:24].view(np.float64)
+        sum_ret, sum_len = float(sums[0]), float(sums[1])
         k = min(n, self.cap)
         if k > g:
-            for name, src in srcs:
-                self._host[name][g:k].copy_(src[g:k], non_blocking=True)
+            host[HDR_BYTES + 24 * g:HDR_BYTES + 24 * k].copy_(self.buf[HDR_BYTES + 24 * g:HDR_BYTES + 24 * k], non_blocking=True)
             torch.cuda.current_stream().synchronize()
         self.clear()
-        self.last_d2h_bytes = 24 + 20 * max(k, g)
-        self._guess = k + k // 4 + 64
-        return n, s[0], s[1], {name: buf[:k].numpy() for name, buf in self._host.items()}
+        self.last_d2h_bytes = HDR_BYTES + 24 * max(k, g)
+        self._guess = min(self.cap, 2 * n + 1024)
+        e = raw[HDR_BYTES:HDR_BYTES + 24 * k].view(ENTRY_DTYPE)
+        return n, sum_ret, sum_len, {"step": e["step"], "env": e["env"], "ret": e["ret"], "len": e["len"]}
+
+    def read_header(self):
+        """(count, sum_ret, sum_len): one 32-byte D2H copy (synchronises the current stream)."""
+        host = self._host[self._flip]
+        host[:HDR_BYTES].copy_(self._hdr, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        raw = host.numpy()
+        sums = raw[8:24].view(np.float64)
+        return int(raw[0:4].view(np.uint32)[0]), float(sums[0]), float(sums[1])
 
     def drain(self, with_entries: bool = True):
-        """D2H read + clear.  Returns (count, sum_ret, sum_len, entries sorted by (step, env))."""
-        n, sum_ret, sum_len = self.read_header()
-        k = min(n, self.cap)
-        entries = []
-        if k and with_entries:
-            st, ev = self.step[:k].tolist(), self.env[:k].tolist()
-            rt, ln = self.ret[:k].tolist(), self.len[:k].tolist()
-            entries = sorted(zip(st, ev, rt, ln))
-        self.clear()
+        """D2H read + clear.  Returns (count, sum_ret, sum_len, entries [(step, env, ret, len)] sorted by (step, env))."""
+        if not with_entries:
+            n, sum_ret, sum_len = self.read_header()
+            self.clear()
+            return n, sum_ret, sum_len, []
+        n, sum_ret, sum_len, a = self.drain_arrays()
+        entries = sorted(zip(a["step"].tolist(), a["env"].tolist(), a["ret"].tolist(), a["len"].tolist()))
         return n, sum_ret, sum_len, entries
 
 

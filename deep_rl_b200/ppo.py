@@ -109,6 +109,22 @@ class _Phase:
         return False
 
 
+class MetricsRead:
+    """Handle of PPOTrainer.metrics_async()."""
+
+    def __init__(self, tr: "PPOTrainer", host_terms: torch.Tensor, log_read):
+        self.tr, self.host_terms, self.log_read = tr, host_terms, log_read
+        self.d2h_bytes = 36 + tr.env.log.last_d2h_bytes
+
+    def result(self) -> Dict[str, object]:
+        n, sum_ret, sum_len, e, lost = self.log_read.result()      # waits for the copies (both precede the event)
+        lt = self.host_terms.tolist()
+        return {"loss": lt[0], "pg_loss": lt[1], "v_loss": lt[2], "entropy": lt[3], "approx_kl": lt[4], "clipfrac": lt[5],
+                "grad_norm": lt[8], "episodes": n, "episodes_dropped": max(0, n - self.tr.env.log.cap) + max(0, min(n, self.tr.env.log.cap) - len(e)),
+                "mean_return": (sum_ret / n) if n else float("nan"), "mean_length": (sum_len / n) if n else float("nan"),
+                "episode_log": {"step": e["step"], "env": e["env"], "ret": e["ret"], "len": e["len"]}}
+
+
 class PPOTrainer:
     """Owns the device buffers of one rank and issues the kernels of one update."""
 
@@ -165,6 +181,8 @@ class PPOTrainer:
         self.loss_terms = self._terms_and_norm[: n_rows * 8].view(n_rows, 8)
         self.grad_norm = self._terms_and_norm[n_rows * 8:]
         self._h_terms = torch.zeros(9, dtype=f32).pin_memory()
+        self._h_terms_ring = [torch.zeros(9, dtype=f32).pin_memory() for _ in range(2)]
+        self._h_flip = 0
         self.ws_bytes = int(self.L.drl_workspace_bytes(C.byref(self.net)))
         self.workspace = torch.zeros(self.ws_bytes, dtype=u8, device=dev)
         self.coef = _lib.PpoCoefT(cfg.clip_coef, cfg.ent_coef, cfg.vf_coef)
@@ -445,6 +463,18 @@ class PPOTrainer:
                 "clipfrac": lt[5], "grad_norm": lt[8], "episodes": n, "episodes_dropped": max(0, n - self.env.log.cap),
                 "mean_return": (sum_ret / n) if n else float("nan"), "mean_length": (sum_len / n) if n else float("nan"),
                 "episode_log": entries}
+
+    def metrics_async(self) -> "MetricsRead":
+        """Enqueue the device->host read of this update's loss terms, gradient norm, episode statistics and finished-episode
+        records (one 36-byte and one header + records copy into pinned memory, then the clear of the log) and return a handle;
+        `handle.result()` waits for the copies only.  Lets a training loop read update k's metrics while update k+1 runs:
+
+            tr.update(); h = tr.metrics_async(); tr.update(); m = h.result(); ...
+        """
+        host = self._h_terms_ring[self._h_flip]
+        self._h_flip ^= 1
+        host.copy_(self._d_terms_src(), non_blocking=True)
+        return MetricsRead(self, host, self.env.log.read_async())
 
     def check_peers(self) -> None:
         """Raises if a peer rank missed the in-kernel all-reduce (the kernels skip the optimizer step from then on).

@@ -47,17 +47,22 @@ typedef struct {
     int32_t* ep_len;             /* [N] running episode length */
 } drl_env_t;
 
-/* Finished-episode log: replaces info["episode"] + the print of ppo.py:130. All fields optional
- * (pass a NULL drl_ep_log_t* to drop the log). */
+/* Finished-episode log: replaces info["episode"] + the print of ppo.py:130.  One 24-byte record per finished episode (array of
+ * structs: the host fetches a prefix of the log with ONE device->host copy).  All fields optional (pass a NULL drl_ep_log_t*
+ * to drop the log). */
 typedef struct {
-    uint32_t* count;     /* [1] episodes finished (atomic; may exceed cap, entries beyond cap dropped) */
-    double*   sum_ret;   /* [1] sum of finished returns */
-    double*   sum_len;   /* [1] sum of finished lengths */
-    float*    log_ret;   /* [cap] */
-    int32_t*  log_len;   /* [cap] */
-    uint32_t* log_env;   /* [cap] global env id */
-    uint64_t* log_step;  /* [cap] global step index (0-based) at which the episode ended */
-    uint32_t  cap;
+    uint64_t step;       /* global step index (0-based) at which the episode ended */
+    uint32_t env;        /* global env id */
+    float    ret;        /* episodic return (float32 like RecordEpisodeStatistics) */
+    int32_t  len;        /* episode length */
+    uint32_t pad;
+} drl_ep_entry_t;
+typedef struct {
+    uint32_t*       count;     /* [1] episodes finished (atomic; may exceed cap, entries beyond cap dropped) */
+    double*         sum_ret;   /* [1] sum of finished returns */
+    double*         sum_len;   /* [1] sum of finished lengths */
+    drl_ep_entry_t* entries;   /* [cap] */
+    uint32_t        cap;
 } drl_ep_log_t;
 
 /* Actor-critic shape (ppo.py:31-47): two separate tanh MLPs O->H->H->A and O->H->H->1. */

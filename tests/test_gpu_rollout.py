@@ -454,3 +454,30 @@ def test_cuda_graph_update_is_bit_identical_to_eager(env_id, N, T):
     e.update(12)
     torch.cuda.synchronize()
     assert torch.equal(g.agent.flat_params, e.agent.flat_params) and torch.equal(g.env.state, e.env.state)
+
+
+def test_metrics_async_reads_what_metrics_reads():
+    """Pipelined reads (update k's metrics consumed while update k+1 runs) return exactly what the synchronous metrics() returns."""
+    import deep_rl_b200 as drl
+    mk = lambda: drl.PPOTrainer(drl.PPOConfig(num_envs=512, num_steps=32, seed=8, total_timesteps=512 * 32 * 12, update_precision="bf16"))
+    a, b = mk(), mk()
+    sync = []
+    for _ in range(6):
+        a.update(12)
+        m = a.metrics(with_episode_log="arrays")
+        sync.append((m["loss"], m["grad_norm"], m["episodes"], m["mean_return"], sorted(zip(m["episode_log"]["step"].tolist(),
+                     m["episode_log"]["env"].tolist(), m["episode_log"]["ret"].tolist(), m["episode_log"]["len"].tolist()))))
+    got, pending = [], None
+    for _ in range(6):
+        b.update(12)
+        h = b.metrics_async()
+        if pending is not None:
+            got.append(pending.result())
+        pending = h
+    got.append(pending.result())
+    assert len(got) == 6
+    for s, m in zip(sync, got):
+        assert m["episodes_dropped"] == 0
+        e = m["episode_log"]
+        assert s == (m["loss"], m["grad_norm"], m["episodes"], m["mean_return"],
+                     sorted(zip(e["step"].tolist(), e["env"].tolist(), e["ret"].tolist(), e["len"].tolist())))
