@@ -61,7 +61,7 @@ class EpisodeLog:
                                   self.buf.data_ptr() + HDR_BYTES, self.cap)
         self._host = [torch.zeros(HDR_BYTES + 24 * self.cap, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self._flip = 0
-        self._guess = min(self.cap, 1024)
+        self._guess = self.cap        # the first read fetches the whole log once; later reads twice the previous count
         self.last_d2h_bytes = 0
 
     # typed views of the record fields (tests, single-env gym API)
