@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include "drl_env.cuh"
+#include "drl_h256.cuh"
 #include "drl_pack.cuh"
 
 namespace drl {
@@ -34,7 +35,10 @@ int sm_count() {
 
 int check_net(const drl_net_t* net) {
     if (net == nullptr) { set_error("net is NULL"); return DRL_ERR_ARG; }
-    if (net->hidden != H) { set_error("hidden=%d unsupported (this build: %d)", net->hidden, H); return DRL_ERR_UNSUPPORTED; }
+    if (net->hidden != H && net->hidden != h256::HH) {
+        set_error("hidden=%d unsupported (this build: %d and %d)", net->hidden, H, h256::HH);
+        return DRL_ERR_UNSUPPORTED;
+    }
     const bool cart = net->obs_dim == 4 && net->num_actions == 2 && net->obs_stride == 4;
     const bool acro = net->obs_dim == 6 && net->num_actions == 3 && net->obs_stride == 8;
     const bool mcar = net->obs_dim == 2 && net->num_actions == 3 && net->obs_stride == 4;
@@ -50,6 +54,11 @@ template <int O, int A>
 __global__ void pack_params_kernel(const float* __restrict__ params, float* __restrict__ packed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < Packed<O, A>::C_ALL) packed_store<O, A>(packed, i, params[i]);
+}
+template <int O, int A>
+__global__ void pack_params256_kernel(const float* __restrict__ params, float* __restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < h256::Packed256<O, A>::C_ALL) h256::packed_store256<O, A>(packed, i, params[i]);
 }
 
 }  // namespace drl
@@ -67,10 +76,14 @@ int drl_env_obs_stride(int32_t kind) { return (kind == DRL_ENV_CARTPOLE || kind 
 
 int64_t drl_param_count(const drl_net_t* net) {
     if (check_net(net) != DRL_OK) return -1;
+    if (net->hidden == h256::HH)
+        return net->obs_dim == 4 ? h256::Packed256<4, 2>::C_ALL : net->obs_dim == 6 ? h256::Packed256<6, 3>::C_ALL : h256::Packed256<2, 3>::C_ALL;
     return net->obs_dim == 4 ? Packed<4, 2>::C_ALL : net->obs_dim == 6 ? Packed<6, 3>::C_ALL : Packed<2, 3>::C_ALL;
 }
 int64_t drl_packed_count(const drl_net_t* net) {
     if (check_net(net) != DRL_OK) return -1;
+    if (net->hidden == h256::HH)
+        return net->obs_dim == 4 ? h256::Packed256<4, 2>::TOTAL : net->obs_dim == 6 ? h256::Packed256<6, 3>::TOTAL : h256::Packed256<2, 3>::TOTAL;
     return net->obs_dim == 4 ? Packed<4, 2>::TOTAL : net->obs_dim == 6 ? Packed<6, 3>::TOTAL : Packed<2, 3>::TOTAL;
 }
 int drl_record_width(const drl_net_t* net) {
@@ -79,7 +92,7 @@ int drl_record_width(const drl_net_t* net) {
 }
 size_t drl_workspace_bytes(const drl_net_t* net) {
     if (check_net(net) != DRL_OK) return 0;
-    return workspace_bytes_for(drl_param_count(net));
+    return workspace_bytes_for(drl_param_count(net), net->hidden);
 }
 
 int drl_pack_params(const drl_net_t* net, const float* params, float* packed_out, void* stream) {
@@ -88,6 +101,13 @@ int drl_pack_params(const drl_net_t* net, const float* params, float* packed_out
     DRL_REQUIRE(params && packed_out, "drl_pack_params: NULL pointer");
     const int P = (int)drl_param_count(net);
     const int blocks = (P + 255) / 256;
+    if (net->hidden == h256::HH) {
+        if (net->obs_dim == 4) pack_params256_kernel<4, 2><<<blocks, 256, 0, as_stream(stream)>>>(params, packed_out);
+        else if (net->obs_dim == 6) pack_params256_kernel<6, 3><<<blocks, 256, 0, as_stream(stream)>>>(params, packed_out);
+        else pack_params256_kernel<2, 3><<<blocks, 256, 0, as_stream(stream)>>>(params, packed_out);
+        DRL_LAUNCH_CHECK("pack_params256_kernel");
+        return DRL_OK;
+    }
     if (net->obs_dim == 4) pack_params_kernel<4, 2><<<blocks, 256, 0, as_stream(stream)>>>(params, packed_out);
     else if (net->obs_dim == 6) pack_params_kernel<6, 3><<<blocks, 256, 0, as_stream(stream)>>>(params, packed_out);
     else pack_params_kernel<2, 3><<<blocks, 256, 0, as_stream(stream)>>>(params, packed_out);

@@ -5,6 +5,11 @@
 
 namespace drl {
 
+namespace h256 {
+int launch_forward256(const drl_net_t* net, const float* packed, const float* obs, int64_t n, float* logits, float* value,
+                      int only_net, cudaStream_t st);     // update256.cu
+}
+
 constexpr int FWD_WARPS = 4;
 
 template <int O, int A, int OP>
@@ -94,6 +99,8 @@ int drl_policy_forward(const drl_net_t* net, const float* packed, const float* o
     if (rc != DRL_OK) return rc;
     DRL_REQUIRE(packed && obs && logits_out && value_out, "drl_policy_forward: NULL pointer");
     if (n <= 0) return DRL_OK;
+    if (net->hidden == 256)      // 256-wide nets exist on the tensor-core path only (bf16 operands, fp32 accumulation)
+        return h256::launch_forward256(net, packed, obs, n, logits_out, value_out, -1, as_stream(stream));
     if (net->obs_dim == 4) return launch_forward<4, 2, 4>(packed, obs, n, logits_out, value_out, as_stream(stream));
     if (net->obs_dim == 2) return launch_forward<2, 3, 4>(packed, obs, n, logits_out, value_out, as_stream(stream));
     return launch_forward<6, 3, 8>(packed, obs, n, logits_out, value_out, as_stream(stream));

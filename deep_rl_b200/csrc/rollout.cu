@@ -16,6 +16,11 @@ drl_ep_log_t log_or_empty(const drl_ep_log_t* log);
 int launch_rollout_tc(const drl_env_t& env, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
                       const drl_ep_log_t& log, cudaStream_t st, const drl_ctrl_t* ctrl);   // rollout_tc.cu
 
+namespace h256 {
+int launch_rollout256(const drl_env_t& env, const drl_net_t* net, const float* packed, int T, uint64_t step0, const drl_rollout_buf_t& buf,
+                      const drl_ep_log_t& log, cudaStream_t st, const drl_ctrl_t* ctrl);     // rollout256.cu
+}
+
 constexpr int RO_WARPS = 4;
 
 template <int KIND, int SUB, int TL>
@@ -157,6 +162,10 @@ static int rollout_impl(const drl_env_t* env, const drl_net_t* net, const float*
                 "drl_rollout: net shape does not match env kind %d", env->kind);
     const drl_ep_log_t l = log_or_empty(log);
     cudaStream_t st = as_stream(stream);
+    if (net->hidden == 256) {
+        DRL_REQUIRE(flags & DRL_ROLLOUT_TENSOR_CORES, "drl_rollout: hidden=256 exists on the tensor-core path only");
+        return h256::launch_rollout256(*env, net, packed, T, step0, *buf, l, st, ctrl);
+    }
     if (flags & DRL_ROLLOUT_TENSOR_CORES) return launch_rollout_tc(*env, packed, T, step0, *buf, l, st, ctrl);
     const int epw = pick_envs_per_warp(env->num_envs);
     if (env->kind == DRL_ENV_CARTPOLE) return dispatch_rollout<DRL_ENV_CARTPOLE>(epw, *env, packed, T, step0, *buf, l, st, ctrl);

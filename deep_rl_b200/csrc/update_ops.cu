@@ -4,11 +4,17 @@
 //                     per-CTA partial gradients (FP32 CUDA-core path)
 //   grad_reduce_kernel fixed-order sum of the per-CTA partials -> flat gradient + loss terms
 //   clip_adam_kernel  clip_grad_norm_ + Adam (+ refresh of the packed kernel layout), ppo.py:191-192
+#include "drl_h256.cuh"
 #include "drl_mlp.cuh"
 #include "drl_pack.cuh"
 #include "drl_update.cuh"
 
 namespace drl {
+
+namespace h256 {
+int launch_grad256(const drl_net_t* net, const GradArgs& g, int P, float* grad_out, float* loss_terms_out, void* workspace,
+                   cudaStream_t st);      // update256.cu
+}
 
 constexpr int GW = 8;                 // warps per CTA
 constexpr int GT = GW * 32;           // threads per CTA
@@ -402,7 +408,13 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const float* __restric
 
 // clip_grad_norm_ + Adam.  Every CTA recomputes the global norm from the (L2-resident) gradient in
 // the same order, so no grid-wide synchronisation is needed and all CTAs agree bit-for-bit.
-template <int O, int A>
+template <int O, int A, int HID>
+__device__ __forceinline__ void packed_store_any(float* __restrict__ packed, int i, float v) {
+    if constexpr (HID == 256) h256::packed_store256<O, A>(packed, i, v);
+    else packed_store<O, A>(packed, i, v);
+}
+
+template <int O, int A, int HID = 64>
 __global__ void __launch_bounds__(256) clip_adam_kernel(AdamArgs a) {
     __shared__ double sh[8];
     __shared__ float s_coef;
@@ -446,7 +458,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(AdamArgs a) {
     const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
     p = p + (a.neg_step_size * m) / denom;                 // param.addcdiv_(exp_avg, denom, value=-step_size)
     a.m[i] = m; a.v[i] = v; a.params[i] = p;
-    if (a.packed != nullptr) packed_store<O, A>(a.packed, i, p);
+    if (a.packed != nullptr) packed_store_any<O, A, HID>(a.packed, i, p);
 }
 
 // Single-GPU tail of a minibatch step in ONE cooperative launch: fixed-order fold of the per-CTA partial gradients,
@@ -584,7 +596,7 @@ static int run_grad(const drl_net_t* net, const float* packed, const float* rec,
     DRL_REQUIRE(packed && rec && adv_stats && coef && grad_out && workspace, "minibatch gradient: NULL pointer");
     DRL_REQUIRE(mb_count > 0, "minibatch gradient: empty minibatch");
     const int P = (int)drl_param_count(net);
-    const WorkspaceLayout w = workspace_layout(P);
+    const WorkspaceLayout w = workspace_layout(P, net->hidden);
     DRL_REQUIRE(workspace_bytes >= w.total, "minibatch gradient: workspace %zu < %zu bytes", workspace_bytes, w.total);
     GradArgs g;
     g.packed = packed; g.rec = rec; g.idx = idx; g.mb_start = mb_start; g.mb_count = mb_count; g.adv_stats = adv_stats;
@@ -596,6 +608,11 @@ static int run_grad(const drl_net_t* net, const float* packed, const float* rec,
     g.tail.enabled = 0;
     g.tail.ctrl = nullptr; g.tail.ordinal = 0;
     if (g_out) { *g_out = g; if (grid_out == nullptr) return DRL_OK; }   // arguments only
+    if (net->hidden == 256) {
+        DRL_REQUIRE(flags & DRL_GRAD_TENSOR_CORES, "minibatch gradient: hidden=256 exists on the tensor-core path only");
+        DRL_REQUIRE(grid_out == nullptr, "minibatch gradient: hidden=256 has no fused fold");
+        return h256::launch_grad256(net, g, P, grad_out, loss_terms_out, workspace, st);
+    }
     if (flags & DRL_GRAD_TENSOR_CORES) return launch_grad_tc(net, g, P, grad_out, loss_terms_out, st, grid_out);
     if (net->obs_dim == 4) return launch_grad<4, 2, 4, 8>(g, P, grad_out, loss_terms_out, st, grid_out);
     if (net->obs_dim == 2) return launch_grad<2, 3, 4, 8>(g, P, grad_out, loss_terms_out, st, grid_out);
@@ -632,6 +649,7 @@ static int minibatch_update_impl(const drl_net_t* net, float* packed, const floa
                                  uint32_t flags, const drl_comm_t* comm, void* stream, const drl_ctrl_t* ctrl = nullptr, int ordinal = 0) {
     int rc = check_net(net);
     if (rc != DRL_OK) return rc;
+    if (net->hidden != H) { set_error("drl_ppo_minibatch_update: hidden=%d has no fused step (use drl_ppo_minibatch_grad + drl_clip_adam)", net->hidden); return DRL_ERR_UNSUPPORTED; }
     DRL_REQUIRE(params && exp_avg && exp_avg_sq, "drl_ppo_minibatch_update: NULL pointer");
     DRL_REQUIRE(step >= 1, "drl_ppo_minibatch_update: step=%lld must be >= 1", (long long)step);
     cudaStream_t st = as_stream(stream);
@@ -787,6 +805,13 @@ int drl_clip_adam(const drl_net_t* net, float* params, const float* grad, float*
     AdamArgs a;
     fill_adam(a, net, params, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, max_grad_norm, grad_scale, packed_out, norm_out);
     const int blocks = (a.P + 255) / 256;
+    if (net->hidden == 256) {
+        if (net->obs_dim == 4) clip_adam_kernel<4, 2, 256><<<blocks, 256, 0, as_stream(stream)>>>(a);
+        else if (net->obs_dim == 2) clip_adam_kernel<2, 3, 256><<<blocks, 256, 0, as_stream(stream)>>>(a);
+        else clip_adam_kernel<6, 3, 256><<<blocks, 256, 0, as_stream(stream)>>>(a);
+        DRL_LAUNCH_CHECK("clip_adam_kernel");
+        return DRL_OK;
+    }
     if (net->obs_dim == 4) clip_adam_kernel<4, 2><<<blocks, 256, 0, as_stream(stream)>>>(a);
     else if (net->obs_dim == 2) clip_adam_kernel<2, 3><<<blocks, 256, 0, as_stream(stream)>>>(a);
     else clip_adam_kernel<6, 3><<<blocks, 256, 0, as_stream(stream)>>>(a);

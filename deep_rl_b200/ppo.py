@@ -186,6 +186,8 @@ class PPOTrainer:
         self.ws_bytes = int(self.L.drl_workspace_bytes(C.byref(self.net)))
         self.workspace = torch.zeros(self.ws_bytes, dtype=u8, device=dev)
         self.coef = _lib.PpoCoefT(cfg.clip_coef, cfg.ent_coef, cfg.vf_coef)
+        if cfg.hidden != 64 and "fp32" in (cfg.resolved_update_precision(), cfg.resolved_rollout_precision()):
+            raise ValueError(f"hidden={cfg.hidden} exists on the tensor-core (bf16) path only")
         if cfg.update_precision not in ("auto", "bf16", "fp32"):
             raise ValueError(f"update_precision={cfg.update_precision!r}")
         if cfg.rollout_precision not in ("auto", "bf16", "fp32"):
@@ -200,9 +202,9 @@ class PPOTrainer:
         self.global_step = 0       # env steps taken on this rank's envs x world (reference counter at N=1)
         self.env.reset()           # ppo.py:101
         self.kernel_launches = 0
-        self.fused_step = True     # single GPU: fold + clip + Adam in one cooperative kernel after the gradient kernel
+        self.fused_step = cfg.hidden == 64     # single GPU: fold + clip + Adam inside the gradient kernel's launch (64-wide nets)
         self.peer = None
-        if (self.world > 1 and cfg.grad_allreduce == "peer" and self.grad_flags == 1
+        if (self.world > 1 and cfg.grad_allreduce == "peer" and self.grad_flags == 1 and cfg.hidden == 64
                 and torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.peer = _dist.PeerComm(self.net, self.rank, self.world, dev)
         self.timing = False        # record CUDA events around each phase (bench.py)
@@ -213,7 +215,7 @@ class PPOTrainer:
         self._graph_launches = 0
         self._graph_warm = 0
         n_opt = cfg.update_epochs * self.n_mb
-        self.graph_ok = bool(cfg.cuda_graph and self.grad_flags == 1 and self.n_mb <= 8 and n_opt <= 64 and not self._merge_stats
+        self.graph_ok = bool(cfg.cuda_graph and self.grad_flags == 1 and cfg.hidden == 64 and self.n_mb <= 8 and n_opt <= 64 and not self._merge_stats
                              and (self.world == 1 or self.peer is not None))
 
     def phase_ms(self) -> Dict[str, Dict[str, float]]:

@@ -52,8 +52,11 @@ def test_shape_queries_and_error_codes():
     assert lib.drl_param_count(C.byref(acro)) == 9476
     assert lib.drl_record_width(C.byref(cart)) == 8 and lib.drl_record_width(C.byref(acro)) == 16
     assert lib.drl_workspace_bytes(C.byref(cart)) > 160 * 9155 * 4
-    bad = L.NetT(4, 256, 2, 4)
-    assert lib.drl_param_count(C.byref(bad)) == -1 and b"hidden=256" in lib.drl_last_error()
+    wide = L.NetT(4, 256, 2, 4)                                 # BASELINE config C5: 256-wide MLP
+    assert lib.drl_param_count(C.byref(wide)) == 134_915
+    assert lib.drl_workspace_bytes(C.byref(wide)) > (512 << 20)  # + the h1 / dz2 staging buffers of update256.cu
+    bad = L.NetT(4, 128, 2, 4)
+    assert lib.drl_param_count(C.byref(bad)) == -1 and b"hidden=128" in lib.drl_last_error()
     # argument validation happens before any CUDA call, so these are safe without a GPU
     assert lib.drl_env_reset(None, 0, 0) == -1
     env = L.EnvT(7, 4, 1, 0, 500, 0, 0, 0, 0)

@@ -23,22 +23,22 @@ def _lib():
     return L
 
 
-def _net(O, A):
+def _net(O, A, H=64):
     L = _lib()
-    return L.NetT(O, 64, A, 4 if O <= 4 else 8)
+    return L.NetT(O, H, A, 4 if O <= 4 else 8)
 
 
-def _pack(params_np, O, A):
+def _pack(params_np, O, A, H=64):
     L = _lib()
-    net = _net(O, A)
+    net = _net(O, A, H)
     p = torch.tensor(np.asarray(params_np, np.float32), device=_dev())
     packed = torch.zeros(int(L.lib().drl_packed_count(C.byref(net))), dtype=torch.float32, device=_dev())
     L.check(L.lib().drl_pack_params(C.byref(net), p.data_ptr(), packed.data_ptr(), L.stream_ptr()))
     return net, p, packed
 
 
-def _rand_params(O, A, seed, scale=1.0):
-    return (po.init_params(O, 64, A, seed) * scale + 0.05 * torch.randn(po.param_count(O, 64, A))).numpy()
+def _rand_params(O, A, seed, scale=1.0, H=64):
+    return (po.init_params(O, H, A, seed) * scale + (0.05 if H == 64 else 0.02) * torch.randn(po.param_count(O, H, A))).numpy()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -281,10 +281,10 @@ def _make_records(obs, act, logp, adv, val, O, RW):
     return rec
 
 
-def _grad_gpu(params, rec, idx, start, count, O, A, coef=(0.2, 0.01, 0.5), stats=None, flags=0):
+def _grad_gpu(params, rec, idx, start, count, O, A, coef=(0.2, 0.01, 0.5), stats=None, flags=0, H=64):
     L = _lib()
     d = _dev()
-    net, p, packed = _pack(params, O, A)
+    net, p, packed = _pack(params, O, A, H)
     t_rec = torch.tensor(rec, device=d)
     t_idx = None if idx is None else torch.tensor(np.asarray(idx, np.int64).astype(np.int32), device=d)
     B = rec.shape[0]
@@ -437,12 +437,12 @@ def _gpu_tanh(x: torch.Tensor) -> torch.Tensor:
     return yd.cpu().reshape(x.shape)
 
 
-def _assert_per_tensor(grad, want, O, A, tol, floor=1e-3):
+def _assert_per_tensor(grad, want, O, A, tol, floor=1e-3, H=64):
     """Relative L2 error of every one of the twelve gradient tensors (a wrong block would hide in the global norm); the
     denominator is floored at `floor` x the whole-gradient norm so that a near-zero tensor cannot blow the ratio up."""
     off, worst = 0, ("", 0.0)
     total = float(np.linalg.norm(want))
-    for name, shp in zip(po.PARAM_NAMES, po.param_shapes(O, 64, A)):
+    for name, shp in zip(po.PARAM_NAMES, po.param_shapes(O, H, A)):
         n = int(np.prod(shp))
         e = float(np.linalg.norm(grad[off:off + n] - want[off:off + n]) / max(np.linalg.norm(want[off:off + n]), floor * total))
         assert e < tol, (name, e)
@@ -576,3 +576,73 @@ def test_clip_adam_world_scale_and_acrobot():
     np.testing.assert_allclose(p.cpu().numpy(), wp, rtol=0, atol=3e-7)
     np.testing.assert_allclose(m.cpu().numpy(), wm, rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(v.cpu().numpy(), wv, rtol=1e-6, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------
+# 256-wide actor-critic (BASELINE config C5): tensor-core path only
+# ------------------------------------------------------------------------------------------------
+def test_h256_shapes():
+    L = _lib()
+    for O, A in ((4, 2), (6, 3), (2, 3)):
+        net = _net(O, A, 256)
+        assert L.lib().drl_param_count(C.byref(net)) == po.param_count(O, 256, A)
+    assert L.lib().drl_param_count(C.byref(_net(4, 2, 256))) == 134_915
+    assert L.lib().drl_param_count(C.byref(_net(4, 2, 128))) == -1
+
+
+@pytest.mark.parametrize("O,A", [(4, 2), (6, 3), (2, 3)])
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 5000, 40_000])
+def test_policy_forward_h256(O, A, n):
+    """drl_policy_forward at hidden = 256 (mlp256_kernel, forward mode): <= 5e-4 from the bf16-emulating oracle with the
+    device's tanh.approx, <= 3e-2 from the fp32 torch maths (deep_rl/ppo.py:49-54)."""
+    L = _lib()
+    torch.manual_seed(n)
+    params = _rand_params(O, A, seed=3, H=256)
+    net, p, packed = _pack(params, O, A, 256)
+    OP = net.obs_stride
+    obs = torch.randn(n, OP) * 1.5
+    obs[:, O:] = 0
+    od = obs.to(_dev())
+    logits = torch.full((n, A), float("nan"), dtype=torch.float32, device=_dev())
+    value = torch.full((n,), float("nan"), dtype=torch.float32, device=_dev())
+    L.check(L.lib().drl_policy_forward(C.byref(net), packed.data_ptr(), od.data_ptr(), n, logits.data_ptr(), value.data_ptr(), L.stream_ptr()))
+    el, ev = po.mlp_forward_bf16_emulated(params, obs[:, :O].numpy(), O, 256, A, tanh_fn=_gpu_tanh)
+    np.testing.assert_allclose(logits.cpu().numpy(), el.numpy(), rtol=0, atol=5e-4)
+    np.testing.assert_allclose(value.cpu().numpy(), ev.numpy(), rtol=0, atol=5e-4)
+    wl, wv = po.mlp_forward(torch.tensor(params), obs[:, :O], O, 256, A)
+    np.testing.assert_allclose(logits.cpu().numpy(), wl.numpy(), rtol=0, atol=3e-2)
+    np.testing.assert_allclose(value.cpu().numpy(), wv.numpy(), rtol=0, atol=3e-2)
+
+
+@pytest.mark.parametrize("O,A,B,M", [(4, 2, 4096, 1024), (4, 2, 70, 70), (4, 2, 129, 129), (6, 3, 3000, 750), (2, 3, 2000, 500), (4, 2, 60_000, 30_000)])
+def test_minibatch_grad_h256_vs_oracles(O, A, B, M):
+    """mlp256_kernel + dw2_gemm256_kernel against the bf16-emulating oracle (every tensor <= 2e-3 relative L2) and against
+    torch autograd in fp32 (bf16 tolerance)."""
+    H = 256
+    rng = np.random.default_rng(B)
+    RW = 8 if O <= 4 else 16
+    params = _rand_params(O, A, seed=5, H=H)
+    obs = rng.normal(size=(B, O)).astype(np.float32)
+    act = rng.integers(0, A, size=B)
+    logits, v = po.mlp_forward(torch.tensor(params), torch.tensor(obs), O, H, A)
+    logp_all = torch.log_softmax(logits, -1).numpy()
+    logp_old = (logp_all[np.arange(B), act] + rng.normal(scale=0.15, size=B)).astype(np.float32)
+    val_old = (v.numpy() + rng.normal(scale=0.3, size=B)).astype(np.float32)
+    adv = rng.normal(size=B).astype(np.float32) * 2 + 0.3
+    ret = adv + val_old
+    rec = _make_records(obs, act, logp_old, adv, val_old, O, RW)
+    idx = clib.permutation(B, 3, 1, 0)
+    for k in range(min(2, B // M)):
+        sel = idx[k * M:(k + 1) * M].astype(np.int64)
+        grad, terms, st = _grad_gpu(params, rec, idx, k * M, M, O, A, flags=1, H=H)
+        wt, wg = po.minibatch_grad_bf16_emulated(params, obs[sel], act[sel], logp_old[sel], adv[sel], val_old[sel], O, H, A,
+                                                 float(st[k, 0]), float(st[k, 1]), tanh_fn=_gpu_tanh)
+        print(f"H=256 O={O} B={B} mb={k}: whole-gradient rel L2 vs emulating oracle {_rel_l2(grad, wg):.2e}")
+        worst = _assert_per_tensor(grad, wg, O, A, tol=2e-3, H=H)
+        print("   worst tensor", worst)
+        np.testing.assert_allclose(terms[:6], wt, rtol=1e-4, atol=2e-5)
+        ft, fg = po.minibatch_loss_and_grad(params, obs[sel], act[sel], logp_old[sel], adv[sel], ret[sel], val_old[sel], O, H, A)
+        np.testing.assert_allclose(terms[:4], ft, rtol=2e-2, atol=5e-3)
+        assert _rel_l2(grad, fg) < 0.1
+        g2, t2, _ = _grad_gpu(params, rec, idx, k * M, M, O, A, flags=1, H=H)
+        assert np.array_equal(grad, g2) and np.array_equal(terms, t2)          # deterministic run to run
