@@ -213,6 +213,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// 1-D TMA bulk copy shared -> global (bulk async-group completion).  The shared-memory source must have been made visible to the
+// async proxy (fence.proxy.async by its writers, then a barrier) before the issuing thread executes this.
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory sources (the sources may be overwritten)
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk groups of this thread have completed (their global writes are performed)
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Stage `nfloats` (multiple of 4) of packed parameters into shared memory with TMA bulk copies issued
 // by thread 0; every thread returns once the bytes have landed.  `bar` is a shared mbarrier slot.
 __device__ __forceinline__ void stage_params(float* dst, const float* __restrict__ src, int nfloats, uint64_t* bar) {

@@ -106,6 +106,7 @@ struct Grad256Args {
     float* logits_out;         // forward mode: [n][A]
     float* value_out;          // forward mode: [n]
     int only_net;              // -1: even CTAs the actor, odd CTAs the critic; 0 / 1: every CTA that net
+    long long* dbg;            // optional cycle stamps of CTA 0 (DRL_TC_DEBUG=1), else nullptr
 };
 
 constexpr int STAGE_TILES = 2048;   // 128-sample tiles per net the staging buffers hold (262,144 samples per pair of launches)

@@ -25,7 +25,8 @@
 namespace drl {
 namespace h256 {
 
-constexpr uint32_t C_Z2 = 0, C_X = 128, C_SB2 = 384, C_SW4 = 416, C_SW1 = 448, TM_COLS = 512;
+// tensor-memory columns: z2 halves, then (with C_X) the 256 columns of dh1 | z1 halves | packed bf16 h1 stash | small accumulators
+constexpr uint32_t C_Z2 = 0, C_X = 128, C_DH = 0, C_H1P = 256, C_SB2 = 384, C_SW4 = 416, C_SW1 = 448, TM_COLS = 512;
 constexpr int A_BLOCK = TC_COMPUTE + 64;   // 16 compute warps + MMA-issuer warp + loader warp
 constexpr int OBS_RING = 2;
 
@@ -51,6 +52,9 @@ struct Smem256 {
     static_assert(OFF_OBS % 128 == 0, "operand tile alignment");
 };
 
+// diagnostics: cycle stamps of CTA 0, compute warp 0 (slot = tile * 16 + event) and issuer warp (256 + ...), DRL_TC_DEBUG=1
+#define H2_STAMP(ev) do { if (g.dbg != nullptr && blockIdx.x == 0 && lane == 0 && k < 8 && (warp == 0 || warp == TC_COMPUTE / 32)) g.dbg[(warp == 0 ? 0 : 256) + k * 16 + (ev)] = clock64(); } while (0)
+
 // MODE 0: gradient (records in, partial gradients out); MODE 1: forward only (observations in, logits / values out)
 template <int O, int A, int OP, int RW, int MODE>
 __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
@@ -67,10 +71,10 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
     unsigned char* tOBS = sm + S::OFF_OBS;
     uint4* sSCAL = reinterpret_cast<uint4*>(sm + S::OFF_SCAL);
     float* xch = reinterpret_cast<float*>(sm + S::OFF_XCH);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 l1, 2 fwd-a, 3 fwd-b, 4 dW4, 5 dh1+db2, 6 dW1
-    uint64_t* ring_full = bars + 7;
-    uint64_t* ring_empty = bars + 7 + OBS_RING;
-    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * OBS_RING);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 l1 (units 0..127), 2 fwd-a, 3 fwd-b, 4 dW4, 5 dh1+db2, 6 dW1, 7 l1 (units 128..255)
+    uint64_t* ring_full = bars + 8;
+    uint64_t* ring_empty = bars + 8 + OBS_RING;
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * OBS_RING);
     float* red = reinterpret_cast<float*>(sm + S::OFF_RED);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
     // ---- prologue ----
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 7; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 8; ++i) mbar_init(bars + i, 1);
 #pragma unroll
         for (int i = 0; i < OBS_RING; ++i) { mbar_init(ring_full + i, 32); mbar_init(ring_empty + i, 1); }
         mbar_fence_init();
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
     if (is_mma_warp) {
         // =========================== MMA-issuer warp ===========================
         const uint32_t aW2 = smem_u32(tW2), aACT = smem_u32(tACT), aW1B = smem_u32(tW1B), aOBS = smem_u32(tOBS);
-        constexpr uint32_t ID_L1 = umma::make_idesc(128, 256, false, false);
+        constexpr uint32_t ID_L1 = umma::make_idesc(128, 128, false, false);
         constexpr uint32_t ID_FWD = umma::make_idesc(128, 128, false, false);
         constexpr uint32_t ID_DH1 = umma::make_idesc(128, 256, false, true);
         constexpr uint32_t ID_N16 = umma::make_idesc(128, 16, true, true);
@@ -176,9 +180,12 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
         for (uint32_t k = 0; k < nmy; ++k) {
             const uint32_t b = k & 1u, acc = k > 0 ? 1u : 0u;
             const uint32_t obsb = aOBS + b * 4096;
+            const uint32_t tile = cin + k * ncn;
+            unsigned char* st_h1 = g.stage_h1 + ((size_t)net * g.stage_tiles + tile) * TILE_BYTES;
+            unsigned char* st_dz = g.stage_dz + ((size_t)net * g.stage_tiles + tile) * TILE_BYTES;
             mbar_wait(ring_full + b, (k >> 1) & 1u);
             umma::fence_after_sync();
-            if (umma::elect_one()) {      // layer 1, K = 16, no swizzle: A = operand tile, B = [W1|b1|W1] (256 rows)
+            if (umma::elect_one()) {      // layer 1, K = 16, no swizzle: A = operand tile, B = [W1|b1|W1], units 0..127 first
                 umma::mma(tmem + C_X, umma::make_desc(obsb, 2048, 128, umma::LAYOUT_NONE),
                           umma::make_desc(aW1B, 4096, 128, umma::LAYOUT_NONE), ID_L1, 0u);
                 umma::commit(bars + 1);
@@ -187,6 +194,16 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
             // forward, first N-half (units 0..127), K-chunk by K-chunk as the h1 chunks arrive
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
+                if (c == 0) {       // z1 of units 0..127 is in registers: layer 1 of units 128..255 into the same 128 columns
+                    named_bar_sync(NB_Z2A, NB_ALL);
+                    umma::fence_after_sync();
+                    if (umma::elect_one()) {
+                        umma::mma(tmem + C_X, umma::make_desc(obsb, 2048, 128, umma::LAYOUT_NONE),
+                                  umma::make_desc(aW1B + 128 * 16, 4096, 128, umma::LAYOUT_NONE), ID_L1, 0u);
+                        umma::commit(bars + 7);
+                    }
+                    __syncwarp();
+                }
                 named_bar_sync(NB_H1 + c, NB_ALL);
                 umma::fence_after_sync();
                 if (umma::elect_one()) {
@@ -196,11 +213,15 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
                                   umma::make_desc(aW2 + c * 32768 + kb * 32, 16, 1024, umma::LAYOUT_SW128), ID_FWD, (c > 0 || kb > 0) ? 1u : 0u);
                     if (c == NCH - 1) umma::commit(bars + 2);
                 }
+                // the chunk is also what dw2_gemm256_kernel reads: one TMA bulk store of its 16 KB shared-memory image
+                if (MODE == 0 && lane == 0) { bulk_s2g(st_h1 + c * SLOT_BYTES, tACT + c * SLOT_BYTES, SLOT_BYTES); bulk_commit_group(); }
                 __syncwarp();
             }
             // forward, second N-half (units 128..255): the first half has been read out of tensor memory
             named_bar_sync(NB_Z2A, NB_ALL);
             umma::fence_after_sync();
+            if (MODE == 0 && lane == 0) bulk_wait_group0();      // staged h1 complete: the ring is rewritten and the staging copy re-read
+            __syncwarp();                                        // only after the commit below has fired
             if (umma::elect_one()) {
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c)
@@ -238,11 +259,14 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
                 if (umma::elect_one()) {
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb)
-                        umma::mma(tmem + C_X, umma::make_desc(aACT + c * SLOT_BYTES + kb * 32, 16, 1024, umma::LAYOUT_SW128),
+                        umma::mma(tmem + C_DH, umma::make_desc(aACT + c * SLOT_BYTES + kb * 32, 16, 1024, umma::LAYOUT_SW128),
                                   umma::make_desc(aW2 + (4 * c + kb) * 2048, 32768, 1024, umma::LAYOUT_SW128), ID_DH1, (c > 0 || kb > 0) ? 1u : 0u);
                 }
+                if (lane == 0) { bulk_s2g(st_dz + c * SLOT_BYTES, tACT + c * SLOT_BYTES, SLOT_BYTES); bulk_commit_group(); }
                 __syncwarp();
             }
+            if (lane == 0) bulk_wait_group_read0();      // the staged dz2 chunks have been read out of the ring (P2 overwrites it)
+            __syncwarp();
             if (umma::elect_one()) {      // db2 += dz2^T . 1 (the ones column of the operand tile)
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
@@ -287,38 +311,49 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
     for (uint32_t k = 0; k < nmy; ++k) {
         const uint32_t par = k & 1u, b = k & 1u;
         const uint32_t tile = cin + k * ncn;
-        unsigned char* st_h1 = g.stage_h1 + ((size_t)net * g.stage_tiles + tile) * TILE_BYTES;
-        unsigned char* st_dz = g.stage_dz + ((size_t)net * g.stage_tiles + tile) * TILE_BYTES;
         const uint32_t off0 = umma::sw128_off(r, 2 * j), off1 = umma::sw128_off(r, 2 * j + 1);     // this thread's two 16-byte units of a chunk row
 
-        // ================= P0: h1 = tanh(z1), chunk by chunk =================
+        // ================= P0: h1 = tanh(z1), chunk by chunk (z1 arrives in two halves of 128 units) =================
+        H2_STAMP(0);
         mbar_wait(bars + 1, par);
         umma::fence_after_sync();
-#pragma unroll 1
+        H2_STAMP(1);
+        float zz[2][16];
+        umma::ld16(trow + C_X + 16 * j, zz[0]);
+        umma::ld16(trow + C_X + 64 + 16 * j, zz[1]);
+        umma::fence_before_sync();
+        named_bar_arrive(NB_Z2A, NB_ALL);          // z1 of units 0..127 is in registers (the barrier is free until the forward GEMM)
+#pragma unroll
         for (int c = 0; c < NCH; ++c) {
-            float z[16];
-            umma::ld16(trow + C_X + 64 * c + 16 * j, z);
+            if (c == 2) {
+                mbar_wait(bars + 7, par);
+                umma::fence_after_sync();
+                umma::ld16(trow + C_X + 16 * j, zz[0]);
+                umma::ld16(trow + C_X + 64 + 16 * j, zz[1]);
+            }
+            float (&z)[16] = zz[c & 1];
 #pragma unroll
             for (int e = 0; e < 16; ++e) z[e] = tanh_mufu(z[e]);
-            uint4 q0, q1;
-            q0.x = umma::pack_bf16(z[0], z[1]); q0.y = umma::pack_bf16(z[2], z[3]); q0.z = umma::pack_bf16(z[4], z[5]); q0.w = umma::pack_bf16(z[6], z[7]);
-            q1.x = umma::pack_bf16(z[8], z[9]); q1.y = umma::pack_bf16(z[10], z[11]); q1.z = umma::pack_bf16(z[12], z[13]); q1.w = umma::pack_bf16(z[14], z[15]);
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pk[e] = umma::pack_bf16(z[2 * e], z[2 * e + 1]);
+            const uint4 q0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), q1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             if (MODE == 0 && c == 0 && k > 0) mbar_wait(bars + 6, (k - 1) & 1u);      // dW1(k-1) has finished reading the ring
             *reinterpret_cast<uint4*>(tACT + c * SLOT_BYTES + off0) = q0;
             *reinterpret_cast<uint4*>(tACT + c * SLOT_BYTES + off1) = q1;
-            if (MODE == 0) {
-                *reinterpret_cast<uint4*>(st_h1 + c * SLOT_BYTES + off0) = q0;
-                *reinterpret_cast<uint4*>(st_h1 + c * SLOT_BYTES + off1) = q1;
-            }
+            if (MODE == 0) umma::st8_raw(trow + C_H1P + 32 * j + 8 * c, pk);         // bf16 h1 stash for P2 (this thread's own columns)
             umma::fence_proxy_async();
             umma::fence_before_sync();
             named_bar_arrive(NB_H1 + c, NB_ALL);
         }
+        if (MODE == 0) umma::wait_st();
 
         // ================= P1: h2 = tanh(z2 + b2) in two halves, heads =================
         float h2[64];      // h2[16 cc + e] = unit 64 cc + 16 j + e
+        H2_STAMP(2);
         mbar_wait(bars + 2, par);
         umma::fence_after_sync();
+        H2_STAMP(3);
         {
             float z[16];
             umma::ld16(trow + C_Z2 + 16 * j, z);
@@ -340,8 +375,10 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
                 h2[16 * cc + 4 * e4 + 2] = tanh_mufu(h2[16 * cc + 4 * e4 + 2] + bb.z);
                 h2[16 * cc + 4 * e4 + 3] = tanh_mufu(h2[16 * cc + 4 * e4 + 3] + bb.w);
             }
+        H2_STAMP(4);
         mbar_wait(bars + 3, par);
         umma::fence_after_sync();
+        H2_STAMP(5);
         {
             float z[16];
             umma::ld16(trow + C_Z2 + 16 * j, z);
@@ -384,7 +421,9 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
                 xch[(j * 3 + a) * TC_TILE + r] = ps[a];
             }
         }
+        H2_STAMP(6);
         named_bar_sync(NB_QUAD + q, 128);
+        H2_STAMP(7);
         float out[A];
 #pragma unroll
         for (int a = 0; a < A; ++a) {
@@ -489,62 +528,61 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
         umma::fence_proxy_async();
         umma::fence_before_sync();
         named_bar_arrive(NB_W4RDY, NB_ALL);
-        // dz2 = (dout . W4) * (1 - h2^2), in place
+        H2_STAMP(8);
+        // dz2 = (dout . W4) * (1 - h2^2), chunk by chunk: the dh1 GEMM of chunk c runs while chunk c + 1 is computed
+        H2_STAMP(9);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
+        for (int c = 0; c < NCH; ++c) {
+            float dz[16];
 #pragma unroll
             for (int e4 = 0; e4 < 4; ++e4) {
                 float dh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int a = 0; a < A; ++a) {
                     if (a < nheads) {
-                        const float4 ww = *reinterpret_cast<const float4*>(sW4 + a * HH + 64 * cc + 16 * j + 4 * e4);
+                        const float4 ww = *reinterpret_cast<const float4*>(sW4 + a * HH + 64 * c + 16 * j + 4 * e4);
                         dh[0] = fmaf(d[a], ww.x, dh[0]); dh[1] = fmaf(d[a], ww.y, dh[1]);
                         dh[2] = fmaf(d[a], ww.z, dh[2]); dh[3] = fmaf(d[a], ww.w, dh[3]);
                     }
                 }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float hv = h2[16 * cc + 4 * e4 + e];
-                    h2[16 * cc + 4 * e4 + e] = dh[e] * fmaf(-hv, hv, 1.0f);
+                    const float hv = h2[16 * c + 4 * e4 + e];
+                    dz[4 * e4 + e] = dh[e] * fmaf(-hv, hv, 1.0f);
                 }
             }
-        mbar_wait(bars + 4, par);          // the dW4 GEMM has consumed the h2 chunks
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
             uint4 q0, q1;
-            q0.x = umma::pack_bf16(h2[16 * c + 0], h2[16 * c + 1]); q0.y = umma::pack_bf16(h2[16 * c + 2], h2[16 * c + 3]);
-            q0.z = umma::pack_bf16(h2[16 * c + 4], h2[16 * c + 5]); q0.w = umma::pack_bf16(h2[16 * c + 6], h2[16 * c + 7]);
-            q1.x = umma::pack_bf16(h2[16 * c + 8], h2[16 * c + 9]); q1.y = umma::pack_bf16(h2[16 * c + 10], h2[16 * c + 11]);
-            q1.z = umma::pack_bf16(h2[16 * c + 12], h2[16 * c + 13]); q1.w = umma::pack_bf16(h2[16 * c + 14], h2[16 * c + 15]);
+            q0.x = umma::pack_bf16(dz[0], dz[1]); q0.y = umma::pack_bf16(dz[2], dz[3]); q0.z = umma::pack_bf16(dz[4], dz[5]); q0.w = umma::pack_bf16(dz[6], dz[7]);
+            q1.x = umma::pack_bf16(dz[8], dz[9]); q1.y = umma::pack_bf16(dz[10], dz[11]); q1.z = umma::pack_bf16(dz[12], dz[13]); q1.w = umma::pack_bf16(dz[14], dz[15]);
+            if (c == 0) {
+                mbar_wait(bars + 4, par);          // the dW4 GEMM has consumed the h2 chunks
+                H2_STAMP(10);
+            }
             *reinterpret_cast<uint4*>(tACT + c * SLOT_BYTES + off0) = q0;
             *reinterpret_cast<uint4*>(tACT + c * SLOT_BYTES + off1) = q1;
-            *reinterpret_cast<uint4*>(st_dz + c * SLOT_BYTES + off0) = q0;
-            *reinterpret_cast<uint4*>(st_dz + c * SLOT_BYTES + off1) = q1;
             umma::fence_proxy_async();
             umma::fence_before_sync();
             named_bar_arrive(NB_DZ2 + c, NB_ALL);
         }
 
         // ================= P2: dz1 = dh1 * (1 - h1^2) =================
-        uint4 hq[NCH][2];      // this thread's h1 values (bf16), re-read from the staging copy (L2): the ring now holds dz2
+        uint32_t hq[NCH][8];   // this thread's h1 values (bf16 pairs) back from their tensor-memory stash
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            hq[c][0] = __ldcg(reinterpret_cast<const uint4*>(st_h1 + c * SLOT_BYTES + off0));
-            hq[c][1] = __ldcg(reinterpret_cast<const uint4*>(st_h1 + c * SLOT_BYTES + off1));
-        }
+        for (int c = 0; c < NCH; ++c) umma::ld8_raw(trow + C_H1P + 32 * j + 8 * c, hq[c]);
+        H2_STAMP(11);
         mbar_wait(bars + 5, par);          // dh1 complete; the db2 GEMM has finished reading the dz2 chunks
         umma::fence_after_sync();
+        H2_STAMP(12);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             float dh[16];
-            umma::ld16(trow + C_X + 64 * c + 16 * j, dh);
+            umma::ld16(trow + C_DH + 64 * c + 16 * j, dh);
             uint4 o4[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const uint4 qv = hq[c][h];
-                const float hv[8] = {umma::bf16_lo(qv.x), umma::bf16_hi(qv.x), umma::bf16_lo(qv.y), umma::bf16_hi(qv.y),
-                                     umma::bf16_lo(qv.z), umma::bf16_hi(qv.z), umma::bf16_lo(qv.w), umma::bf16_hi(qv.w)};
+                const uint32_t* qv = hq[c] + 4 * h;
+                const float hv[8] = {umma::bf16_lo(qv[0]), umma::bf16_hi(qv[0]), umma::bf16_lo(qv[1]), umma::bf16_hi(qv[1]),
+                                     umma::bf16_lo(qv[2]), umma::bf16_hi(qv[2]), umma::bf16_lo(qv[3]), umma::bf16_hi(qv[3])};
                 float z[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) z[e] = dh[8 * h + e] * fmaf(-hv[e], hv[e], 1.0f);
@@ -557,6 +595,7 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
         umma::fence_proxy_async();
         umma::fence_before_sync();
         named_bar_arrive(NB_DZ1, NB_ALL);
+        H2_STAMP(13);
     }
 
     if (MODE == 1) {
@@ -722,7 +761,7 @@ static int launch_grad256_t(const GradArgs& g0, int P, float* grad_out, float* l
     a.stage_dz = a.stage_h1 + (size_t)2 * STAGE_TILES * TILE_BYTES;
     a.stage_tiles = STAGE_TILES;
     a.grad_part = g0.grad_part; a.loss_part = g0.loss_part; a.ppad = g0.ppad;
-    a.logits_out = nullptr; a.value_out = nullptr; a.only_net = -1;
+    a.logits_out = nullptr; a.value_out = nullptr; a.only_net = -1; a.dbg = g0.dbg;
     const uint32_t chunk = (uint32_t)STAGE_TILES * TC_TILE;
     for (uint32_t off = 0; off < g0.mb_count; off += chunk) {
         a.mb_start = g0.mb_start + off;

