@@ -106,6 +106,7 @@ struct Grad256Args {
     float* logits_out;         // forward mode: [n][A]
     float* value_out;          // forward mode: [n]
     int only_net;              // -1: even CTAs the actor, odd CTAs the critic; 0 / 1: every CTA that net
+    int first;                 // 1: first launch of this minibatch: the CTA WRITES its partial sums instead of adding to them
     long long* dbg;            // optional cycle stamps of CTA 0 (DRL_TC_DEBUG=1), else nullptr
 };
 

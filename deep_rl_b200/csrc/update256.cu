@@ -611,21 +611,23 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
     float* part = g.grad_part + (size_t)blockIdx.x * g.ppad;
     const int base = net * P::C_ACTOR;
     const int nout = net == 0 ? A : 1;
+    const float keep = g.first ? 0.0f : 1.0f;      // first launch of the minibatch: overwrite the row (it holds the previous minibatch)
+    auto accum = [&](int i, float v) { part[i] = g.first ? v : part[i] + v; };
     if (warp < 4) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int o = 128 * u + r;
             float v16[16];
             umma::ld16(trow + C_SB2 + 16 * u, v16);
-            part[base + HH * O + HH + HH * HH + o] += v16[O];                                   // db2
+            accum(base + HH * O + HH + HH * HH + o, v16[O]);                                    // db2
             umma::ld16(trow + C_SW1 + 16 * u, v16);
 #pragma unroll
-            for (int i = 0; i < O; ++i) part[base + o * O + i] += v16[i] + v16[8 + i];          // dW1 = dz1^T . (obs_hi + obs_lo)
-            part[base + HH * O + o] += v16[O];                                                  // db1
+            for (int i = 0; i < O; ++i) accum(base + o * O + i, v16[i] + v16[8 + i]);           // dW1 = dz1^T . (obs_hi + obs_lo)
+            accum(base + HH * O + o, v16[O]);                                                   // db1
             umma::ld16(trow + C_SW4 + 16 * u, v16);
 #pragma unroll
             for (int a = 0; a < A; ++a)
-                if (a < nout) part[base + P::C_NET + a * HH + o] += v16[dout_col(O, a)];         // dW4
+                if (a < nout) accum(base + P::C_NET + a * HH + o, v16[dout_col(O, a)]);          // dW4
         }
     }
     {
@@ -642,8 +644,8 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
         float sv = 0.0f;
 #pragma unroll
         for (int w = 0; w < TC_COMPUTE / 32; ++w) sv += red[w * 12 + tid];
-        if (tid < 5) g.loss_part[blockIdx.x * LOSS_TERMS + tid] += sv;
-        else if (tid - 5 < nout) part[base + P::C_NET + nout * HH + (tid - 5)] += sv;          // head biases
+        if (tid < 5) g.loss_part[blockIdx.x * LOSS_TERMS + tid] = keep * g.loss_part[blockIdx.x * LOSS_TERMS + tid] + sv;
+        else if (tid - 5 < nout) accum(base + P::C_NET + nout * HH + (tid - 5), sv);            // head biases
     }
     if (warp == 1) umma::tmem_dealloc(tmem, TM_COLS);
 }
@@ -658,7 +660,7 @@ constexpr int B_BLOCK = 192;              // producer warp, issuer warp, four ep
 __global__ void __launch_bounds__(B_BLOCK, 1) dw2_gemm256_kernel(const unsigned char* __restrict__ stage_dz,
                                                                  const unsigned char* __restrict__ stage_h1, uint32_t stage_tiles,
                                                                  uint32_t ntiles, float* __restrict__ grad_part, int ppad, int c_actor,
-                                                                 int w2_off) {
+                                                                 int w2_off, int first) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + B_STAGES * B_STAGE_BYTES);     // full[3], empty[3], done
@@ -724,22 +726,80 @@ __global__ void __launch_bounds__(B_BLOCK, 1) dw2_gemm256_kernel(const unsigned 
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         mbar_wait(bars + 2 * B_STAGES, 0);
         umma::fence_after_sync();
+        // The accumulator row of a thread is one row of dW2 (1 KB): written straight from registers, a warp would touch 32
+        // different lines per instruction.  Each 32 x 32 block goes through shared memory instead (the stage ring is idle now)
+        // and leaves as 32 coalesced 128-byte rows.
         float* part = grad_part + (size_t)blockIdx.x * ppad + net * c_actor + w2_off;
+        float* tile = reinterpret_cast<float*>(sm) + (warp - 2) * (32 * 33);
 #pragma unroll 1
         for (int u = 0; u < 2; ++u) {
-            float* dst = part + (size_t)(128 * u + r) * HH;
 #pragma unroll 1
             for (int cb = 0; cb < 8; ++cb) {
                 float v[32];
                 umma::ld32(trow + 256 * u + 32 * cb, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dst[32 * cb + i] += v[i];
+                for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = v[i];
+                __syncwarp();
+                float* dst = part + (size_t)(128 * u + 32 * q) * HH + 32 * cb + lane;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) {
+                    const float x = tile[rr * 33 + lane];
+                    dst[(size_t)rr * HH] = first ? x : dst[(size_t)rr * HH] + x;
+                }
+                __syncwarp();
             }
         }
         umma::fence_before_sync();
     }
     __syncthreads();
     if (warp == 2) umma::tmem_dealloc(tmem, 512);
+}
+
+// Fixed-order fold of the per-CTA partial rows.  Parameter p of the actor is summed over the even rows, of the critic over the odd
+// rows (the other rows never wrote it).  blockDim = (32, 8): thread (x, y) folds rows first + 2 (y + 8 k), then the 8 slices are
+// folded through shared memory in slice order -- the association of grad_reduce_kernel (update_ops.cu).
+__global__ void __launch_bounds__(256) grad_reduce256_kernel(const float* __restrict__ grad_part, const float* __restrict__ loss_part,
+                                                              int nrows, int ppad, int P, int c_actor, uint32_t mb_count, float ent_coef,
+                                                              float vf_coef, float* __restrict__ grad_out, float* __restrict__ loss_terms_out) {
+    __shared__ float sh[8][33];
+    const int p = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.0f;
+    if (p < P) {
+        const int first = p >= c_actor ? 1 : 0;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int c = first + 2 * threadIdx.y;
+        for (; c + 48 < nrows; c += 64) {
+            const float v0 = __ldcg(grad_part + (size_t)c * ppad + p);
+            const float v1 = __ldcg(grad_part + (size_t)(c + 16) * ppad + p);
+            const float v2 = __ldcg(grad_part + (size_t)(c + 32) * ppad + p);
+            const float v3 = __ldcg(grad_part + (size_t)(c + 48) * ppad + p);
+            a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+        }
+        for (; c < nrows; c += 16) a0 += __ldcg(grad_part + (size_t)c * ppad + p);
+        s = (a0 + a1) + (a2 + a3);
+    }
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && p < P) {
+        float t = sh[0][threadIdx.x];
+#pragma unroll
+        for (int y = 1; y < 8; ++y) t += sh[y][threadIdx.x];
+        grad_out[p] = t;
+    }
+    if (blockIdx.x == 0 && threadIdx.y == 1 && threadIdx.x < 5 && loss_terms_out != nullptr) {
+        float t = 0.f;
+        for (int c = 0; c < nrows; ++c) t += __ldcg(loss_part + c * LOSS_TERMS + threadIdx.x);
+        const float inv = 1.0f / (float)mb_count;
+        const float t0 = __shfl_sync(0x1fu, t, 0), t1 = __shfl_sync(0x1fu, t, 1), t2 = __shfl_sync(0x1fu, t, 2);
+        const float t3 = __shfl_sync(0x1fu, t, 3), t4 = __shfl_sync(0x1fu, t, 4);
+        if (threadIdx.x == 0) {
+            const float pg = t0 * inv, vl = 0.5f * t1 * inv, en = t2 * inv;
+            loss_terms_out[0] = pg - ent_coef * en + vl * vf_coef;
+            loss_terms_out[1] = pg; loss_terms_out[2] = vl; loss_terms_out[3] = en;
+            loss_terms_out[4] = t3 * inv; loss_terms_out[5] = t4 * inv;
+            loss_terms_out[6] = 0.0f; loss_terms_out[7] = 0.0f;
+        }
+    }
 }
 
 template <int O, int A, int OP, int RW>
@@ -752,8 +812,6 @@ static int launch_grad256_t(const GradArgs& g0, int P, float* grad_out, float* l
     const int smem_b = B_STAGES * B_STAGE_BYTES + 128 + 1024;
     DRL_CUDA(cudaFuncSetAttribute(mlp256_kernel<O, A, OP, RW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
     DRL_CUDA(cudaFuncSetAttribute(dw2_gemm256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
-    DRL_CUDA(cudaMemsetAsync(g0.grad_part, 0, sizeof(float) * (size_t)grid * g0.ppad, st));
-    DRL_CUDA(cudaMemsetAsync(g0.loss_part, 0, sizeof(float) * (size_t)grid * LOSS_TERMS, st));
     Grad256Args a;
     a.packed = g0.packed; a.rec = g0.rec; a.idx = g0.idx; a.mb_total = g0.mb_count; a.adv_stats = g0.adv_stats;
     a.clip_coef = g0.clip_coef; a.ent_coef = g0.ent_coef; a.vf_coef = g0.vf_coef;
@@ -767,13 +825,21 @@ static int launch_grad256_t(const GradArgs& g0, int P, float* grad_out, float* l
         a.mb_start = g0.mb_start + off;
         a.mb_count = g0.mb_count - off < chunk ? g0.mb_count - off : chunk;
         const uint32_t ntiles = (a.mb_count + TC_TILE - 1) / TC_TILE;
+        a.first = off == 0 ? 1 : 0;
         mlp256_kernel<O, A, OP, RW, 0><<<grid, A_BLOCK, smem_a, st>>>(a);
         DRL_LAUNCH_CHECK("mlp256_kernel");
         dw2_gemm256_kernel<<<grid, B_BLOCK, smem_b, st>>>(a.stage_dz, a.stage_h1, a.stage_tiles, ntiles, a.grad_part, a.ppad,
-                                                        Packed256<O, A>::C_ACTOR, Packed256<O, A>::W2_OFF);
+                                                        Packed256<O, A>::C_ACTOR, Packed256<O, A>::W2_OFF, a.first);
         DRL_LAUNCH_CHECK("dw2_gemm256_kernel");
     }
-    return launch_grad_reduce(g0, grid, P, grad_out, loss_terms_out, st);
+    // rows that took part: CTA c works iff (c >> 1) < tiles of the (largest = first) chunk; even rows hold actor entries, odd
+    // rows critic entries, so each parameter is folded over the rows of its own net only
+    const uint32_t first_tiles = ((g0.mb_count < chunk ? g0.mb_count : chunk) + TC_TILE - 1) / TC_TILE;
+    const int active = (int)(2 * first_tiles < (uint32_t)grid ? 2 * first_tiles : (uint32_t)grid);
+    grad_reduce256_kernel<<<(P + 31) / 32, dim3(32, 8), 0, st>>>(g0.grad_part, g0.loss_part, active, g0.ppad, P, Packed256<O, A>::C_ACTOR,
+                                                              g0.mb_count, g0.ent_coef, g0.vf_coef, grad_out, loss_terms_out);
+    DRL_LAUNCH_CHECK("grad_reduce256_kernel");
+    return DRL_OK;
 }
 
 int launch_grad256(const drl_net_t* net, const GradArgs& g, int P, float* grad_out, float* loss_terms_out, void* workspace,
