@@ -26,7 +26,7 @@ namespace drl {
 namespace h256 {
 
 // tensor-memory columns: z2 halves, then (with C_X) the 256 columns of dh1 | z1 halves | packed bf16 h1 stash | small accumulators
-constexpr uint32_t C_Z2 = 0, C_X = 128, C_DH = 0, C_H1P = 256, C_SB2 = 384, C_SW4 = 416, C_SW1 = 448, TM_COLS = 512;
+constexpr uint32_t C_Z2 = 0, C_X = 128, C_DH = 0, C_H1P = 256, C_SW4 = 416, C_SW1 = 448, TM_COLS = 512;
 constexpr int A_BLOCK = TC_COMPUTE + 64;   // 16 compute warps + MMA-issuer warp + loader warp
 constexpr int OBS_RING = 2;
 
@@ -177,20 +177,26 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
         constexpr uint32_t ID_DH1 = umma::make_idesc(128, 256, false, true);
         constexpr uint32_t ID_N16 = umma::make_idesc(128, 16, true, true);
         mbar_wait(bars, 0);
+        // layer 1, K = 16, no swizzle: A = operand tile, B = [W1|b1|W1]; units 0..127 first.  Issued for tile k + 1 as soon as the
+        // upper half of the dh1 columns (which it overwrites) has been read in P2 of tile k.
+        auto issue_l1a = [&](uint32_t kk) {
+            const uint32_t bb = kk & 1u;
+            mbar_wait(ring_full + bb, (kk >> 1) & 1u);
+            umma::fence_after_sync();
+            if (umma::elect_one()) {
+                umma::mma(tmem + C_X, umma::make_desc(aOBS + bb * 4096, 2048, 128, umma::LAYOUT_NONE),
+                          umma::make_desc(aW1B, 4096, 128, umma::LAYOUT_NONE), ID_L1, 0u);
+                umma::commit(bars + 1);
+            }
+            __syncwarp();
+        };
+        issue_l1a(0);
         for (uint32_t k = 0; k < nmy; ++k) {
             const uint32_t b = k & 1u, acc = k > 0 ? 1u : 0u;
             const uint32_t obsb = aOBS + b * 4096;
             const uint32_t tile = cin + k * ncn;
             unsigned char* st_h1 = g.stage_h1 + ((size_t)net * g.stage_tiles + tile) * TILE_BYTES;
             unsigned char* st_dz = g.stage_dz + ((size_t)net * g.stage_tiles + tile) * TILE_BYTES;
-            mbar_wait(ring_full + b, (k >> 1) & 1u);
-            umma::fence_after_sync();
-            if (umma::elect_one()) {      // layer 1, K = 16, no swizzle: A = operand tile, B = [W1|b1|W1], units 0..127 first
-                umma::mma(tmem + C_X, umma::make_desc(obsb, 2048, 128, umma::LAYOUT_NONE),
-                          umma::make_desc(aW1B, 4096, 128, umma::LAYOUT_NONE), ID_L1, 0u);
-                umma::commit(bars + 1);
-            }
-            __syncwarp();
             // forward, first N-half (units 0..127), K-chunk by K-chunk as the h1 chunks arrive
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
@@ -236,6 +242,7 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
             if (MODE == 1) {
                 if (umma::elect_one()) umma::commit(ring_empty + b);
                 __syncwarp();
+                if (k + 1 < nmy) issue_l1a(k + 1);       // z1 of this tile was read long ago
                 continue;
             }
             // dW4 += h2^T . dout   (h2 chunks in the ring, dout in the free columns of the operand tile)
@@ -267,16 +274,12 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
             }
             if (lane == 0) bulk_wait_group_read0();      // the staged dz2 chunks have been read out of the ring (P2 overwrites it)
             __syncwarp();
-            if (umma::elect_one()) {      // db2 += dz2^T . 1 (the ones column of the operand tile)
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-#pragma unroll
-                    for (int kb = 0; kb < 8; ++kb)
-                        umma::mma(tmem + C_SB2 + 16 * u, umma::make_desc(aACT + u * 2 * SLOT_BYTES + kb * 2048, SLOT_BYTES, 1024, umma::LAYOUT_SW128),
-                                  umma::make_desc(obsb + kb * 256, 128, 2048, umma::LAYOUT_NONE), ID_N16, acc | (kb > 0 ? 1u : 0u));
-                umma::commit(bars + 5);
-            }
+            if (umma::elect_one()) umma::commit(bars + 5);      // dh1 complete (db2 = column sums of dz2 comes from dw2_gemm256_kernel)
             __syncwarp();
+            if (k + 1 < nmy) {       // dh1 columns 128..255 are in registers: layer 1 of the next tile may overwrite them
+                named_bar_sync(NB_Z2A, NB_ALL);
+                issue_l1a(k + 1);
+            }
             // [dW1|db1] += dz1^T . [obs|1]
             named_bar_sync(NB_DZ1, NB_ALL);
             umma::fence_after_sync();
@@ -570,27 +573,40 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) umma::ld8_raw(trow + C_H1P + 32 * j + 8 * c, hq[c]);
         H2_STAMP(11);
-        mbar_wait(bars + 5, par);          // dh1 complete; the db2 GEMM has finished reading the dz2 chunks
+        mbar_wait(bars + 5, par);          // dh1 complete (and the ring's dz2 chunks staged)
         umma::fence_after_sync();
         H2_STAMP(12);
+        {
+            float dhu[2][16];          // chunks 2, 3 first: their columns are where layer 1 of the next tile goes
+            umma::ld16(trow + C_DH + 64 * 2 + 16 * j, dhu[0]);
+            umma::ld16(trow + C_DH + 64 * 3 + 16 * j, dhu[1]);
+            umma::fence_before_sync();
+            if (k + 1 < nmy) named_bar_arrive(NB_Z2A, NB_ALL);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            float dh[16];
-            umma::ld16(trow + C_DH + 64 * c + 16 * j, dh);
-            uint4 o4[2];
+            for (int cc = 0; cc < NCH; ++cc) {
+                const int c = (cc + 2) & 3;
+                float dh[16];
+                if (cc < 2) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t* qv = hq[c] + 4 * h;
-                const float hv[8] = {umma::bf16_lo(qv[0]), umma::bf16_hi(qv[0]), umma::bf16_lo(qv[1]), umma::bf16_hi(qv[1]),
-                                     umma::bf16_lo(qv[2]), umma::bf16_hi(qv[2]), umma::bf16_lo(qv[3]), umma::bf16_hi(qv[3])};
-                float z[8];
+                    for (int e = 0; e < 16; ++e) dh[e] = dhu[cc][e];
+                } else {
+                    umma::ld16(trow + C_DH + 64 * c + 16 * j, dh);
+                }
+                uint4 o4[2];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) z[e] = dh[8 * h + e] * fmaf(-hv[e], hv[e], 1.0f);
-                o4[h].x = umma::pack_bf16(z[0], z[1]); o4[h].y = umma::pack_bf16(z[2], z[3]);
-                o4[h].z = umma::pack_bf16(z[4], z[5]); o4[h].w = umma::pack_bf16(z[6], z[7]);
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t* qv = hq[c] + 4 * h;
+                    const float hv[8] = {umma::bf16_lo(qv[0]), umma::bf16_hi(qv[0]), umma::bf16_lo(qv[1]), umma::bf16_hi(qv[1]),
+                                         umma::bf16_lo(qv[2]), umma::bf16_hi(qv[2]), umma::bf16_lo(qv[3]), umma::bf16_hi(qv[3])};
+                    float z[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) z[e] = dh[8 * h + e] * fmaf(-hv[e], hv[e], 1.0f);
+                    o4[h].x = umma::pack_bf16(z[0], z[1]); o4[h].y = umma::pack_bf16(z[2], z[3]);
+                    o4[h].z = umma::pack_bf16(z[4], z[5]); o4[h].w = umma::pack_bf16(z[6], z[7]);
+                }
+                *reinterpret_cast<uint4*>(tACT + c * SLOT_BYTES + off0) = o4[0];
+                *reinterpret_cast<uint4*>(tACT + c * SLOT_BYTES + off1) = o4[1];
             }
-            *reinterpret_cast<uint4*>(tACT + c * SLOT_BYTES + off0) = o4[0];
-            *reinterpret_cast<uint4*>(tACT + c * SLOT_BYTES + off1) = o4[1];
         }
         umma::fence_proxy_async();
         umma::fence_before_sync();
@@ -618,8 +634,6 @@ __global__ void __launch_bounds__(A_BLOCK, 1) mlp256_kernel(Grad256Args g) {
         for (int u = 0; u < 2; ++u) {
             const int o = 128 * u + r;
             float v16[16];
-            umma::ld16(trow + C_SB2 + 16 * u, v16);
-            accum(base + HH * O + HH + HH * HH + o, v16[O]);                                    // db2
             umma::ld16(trow + C_SW1 + 16 * u, v16);
 #pragma unroll
             for (int i = 0; i < O; ++i) accum(base + o * O + i, v16[i] + v16[8 + i]);           // dW1 = dz1^T . (obs_hi + obs_lo)
@@ -674,7 +688,8 @@ __global__ void __launch_bounds__(B_BLOCK, 1) dw2_gemm256_kernel(const unsigned 
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 2 * B_STAGES + 1; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < B_STAGES; ++i) { mbar_init(bars + i, 1); mbar_init(bars + B_STAGES + i, 1 + 4); }   // empty: MMA commit + 4 warps
+        mbar_init(bars + 2 * B_STAGES, 1);
         mbar_fence_init();
     }
     if (warp == 2) umma::tmem_alloc(slot, 512);
@@ -720,7 +735,29 @@ __global__ void __launch_bounds__(B_BLOCK, 1) dw2_gemm256_kernel(const unsigned 
             __syncwarp();
         }
     } else {
-        // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+        // warps 2..5.  During the main loop: db2 = column sums of dz2 -- warp w owns chunk w - 2 (64 units), lane l the unit pair
+        // (2l, 2l + 1) = one 32-bit word of every row of the chunk's SW128 image.
+        const int cw = warp - 2;
+        float sb0 = 0.0f, sb1 = 0.0f;
+        for (uint32_t it = 0; it < nit; ++it) {
+            const uint32_t s = it % B_STAGES, use = it / B_STAGES;
+            mbar_wait(bars + s, use & 1u);
+            const unsigned char* ch = sm + s * B_STAGE_BYTES + cw * 8192;
+#pragma unroll 8
+            for (int rr = 0; rr < 64; ++rr) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(ch + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + (lane & 3) * 4);
+                sb0 += umma::bf16_lo(w);
+                sb1 += umma::bf16_hi(w);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + B_STAGES + s);
+        }
+        {
+            float* pb2 = grad_part + (size_t)blockIdx.x * ppad + net * c_actor + w2_off + HH * HH + 64 * cw + 2 * lane;
+            pb2[0] = first ? sb0 : pb2[0] + sb0;
+            pb2[1] = first ? sb1 : pb2[1] + sb1;
+        }
+        // epilogue: TMEM lane quadrant = warp % 4
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
