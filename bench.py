@@ -282,7 +282,8 @@ def _grad_roofline(env_id, hidden, M, phases, total_ms, value, world, tc, peaks,
     g = phases.get("minibatch_grad", {"mean_ms": float("nan"), "total_ms": 0.0})
     flops_per_launch = 3 * F * M
     achieved_tf = flops_per_launch / (g["mean_ms"] * 1e-3) / 1e12
-    return {"kernel": ("ppo_grad_tc_kernel" if tc else "ppo_grad_kernel (+grad_reduce_kernel)") if hidden == 64 else "ppo_grad256 kernels",
+    return {"kernel": ("ppo_grad_tc_kernel" if tc else "ppo_grad_kernel (+grad_reduce_kernel)") if hidden == 64 else
+            "mlp256_kernel + dw2_gemm256_kernel + grad_reduce256_kernel (one drl_ppo_minibatch_grad call)",
             "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
             "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": traffic,
             "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
@@ -371,6 +372,23 @@ def _run_config(name, env_id, envs, T, hidden, steps, warm, rank, world, dev, fl
            "rooflines": _hbm_rooflines(env_id, envs, T, cfg.update_epochs, phases, peaks),
            "phases_ms_per_update": {k: v["total_ms"] / inst_steps for k, v in phases.items()}, "gpu_launches": launches,
            "cuda_graph": tr._graph is not None}
+    if hidden == 256:      # gather-only split = one pass of the keyed-permutation gather over the packed records
+        import ctypes as C
+        from deep_rl_b200 import _lib
+        net = C.byref(tr.net)
+        B, M = cfg.batch_size, cfg.minibatch_size
+        call = lambda: _lib.check(tr.L.drl_adv_stats(net, tr.records.data_ptr(), tr.idx[0].data_ptr(), B, M, tr.adv_stats[0].data_ptr(),
+                                                    tr.workspace.data_ptr(), tr.ws_bytes, _lib.stream_ptr()))
+        call()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); call(); e1.record()
+        torch.cuda.synchronize()
+        gms = e0.elapsed_time(e1)
+        rec["splits_ms_per_update"] = {"gae_only": rec["phases_ms_per_update"].get("gae"), "update_only": rec["phases_ms_per_update"].get("minibatch_grad", 0.0)
+                                       + rec["phases_ms_per_update"].get("clip_adam", 0.0) + rec["phases_ms_per_update"].get("allreduce", 0.0),
+                                       "rollout_only": rec["phases_ms_per_update"].get("rollout"),
+                                       "gather_only_one_epoch": gms, "gather_only_gbs": 36.0 * B / (gms * 1e-3) / 1e9,
+                                       "gather_note": "random 32-byte record + 4-byte index per sample (drl_adv_stats, gather form), one epoch"}
     if tr.peer is not None:
         tr.peer.close()
     del tr
@@ -546,7 +564,7 @@ def run_b200(args):
             fp32_path = {"value": f32["value"], "unit": "env-steps/s", "ms_per_step": f32["ms_per_step"], "workload": workload}
             if args.hidden256:
                 extra.append(_run_config("C5: synthetic stress, 1M envs x 256 steps, 256-wide MLP, 1xB200", "CartPole-v1", 1 << 20, 256, 256,
-                                         2, 1, 0, 1, dev, flush, dist, peaks))
+                                         2, 1, 0, 1, dev, flush, dist, peaks, grad_allreduce="nccl"))
         else:
             per = 16_384 // world
             extra.append(_run_config(f"C4 strong scaling: Acrobot-v1, 16,384 envs total ({per}/GPU) x 256 steps", "Acrobot-v1", per, 256, 64, xs, 3,
@@ -555,7 +573,7 @@ def run_b200(args):
                                      rank, world, dev, flush, dist, peaks))
             if args.hidden256:
                 extra.append(_run_config(f"C5: synthetic stress, 1M envs total ({(1 << 20) // world}/GPU) x 256 steps, 256-wide MLP",
-                                         "CartPole-v1", (1 << 20) // world, 256, 256, 3, 1, rank, world, dev, flush, dist, peaks))
+                                         "CartPole-v1", (1 << 20) // world, 256, 256, 3, 1, rank, world, dev, flush, dist, peaks, grad_allreduce="nccl"))
 
     if rank != 0:
         dist.shutdown()
@@ -634,7 +652,8 @@ def main():
     ap.add_argument("--no-scaling-reference", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip C3-on-one-GPU / C4 / C5 / fp32 / env-step records")
     ap.add_argument("--hidden", type=int, default=64)
-    ap.add_argument("--hidden256", action="store_true", default=False, help="add the C5 (256-wide MLP) record to extra_configs")
+    ap.add_argument("--no-hidden256", dest="hidden256", action="store_false", default=True,
+                    help="skip the C5 (1M envs x 256 steps, 256-wide MLP) record of extra_configs")
     ap.add_argument("--grad-allreduce", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU gradient exchange: in-kernel NVLink peer-memory all-reduce, or NCCL between kernels")
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"],

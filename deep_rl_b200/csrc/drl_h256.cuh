@@ -110,7 +110,7 @@ struct Grad256Args {
     long long* dbg;            // optional cycle stamps of CTA 0 (DRL_TC_DEBUG=1), else nullptr
 };
 
-constexpr int STAGE_TILES = 2048;   // 128-sample tiles per net the staging buffers hold (262,144 samples per pair of launches)
+constexpr int STAGE_TILES = 4096;   // 128-sample tiles per net the staging buffers hold (524,288 samples per pair of launches)
 
 }  // namespace h256
 }  // namespace drl

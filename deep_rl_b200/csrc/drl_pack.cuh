@@ -74,7 +74,7 @@ struct WorkspaceLayout {
     size_t counters, stat_partials, cta_sumsq, loss_partials, grad_partials, debug, ev_partials, stage, total;
     int ppad;
 };
-// hidden = 256 adds the staging buffers of update256.cu: h1 and dz2 of 2 nets x 2048 tiles x 64 KB = 512 MB
+// hidden = 256 adds the staging buffers of update256.cu: h1 and dz2 of 2 nets x 4096 tiles x 64 KB = 1 GB
 inline WorkspaceLayout workspace_layout(int64_t P, int hidden = 64) {
     WorkspaceLayout w;
     w.ppad = (int)((P + 3) / 4 * 4);
@@ -89,7 +89,7 @@ inline WorkspaceLayout workspace_layout(int64_t P, int hidden = 64) {
     w.grad_partials = w.loss_partials + sizeof(float) * MAX_GRAD_CTAS * LOSS_TERMS;
     w.debug = w.grad_partials + sizeof(float) * (size_t)MAX_GRAD_CTAS * w.ppad;   // 4 KB of cycle stamps (DRL_TC_DEBUG=1)
     w.stage = (w.debug + 4096 + 1023) / 1024 * 1024;
-    w.total = w.stage + (hidden == 256 ? (size_t)2 * 2 * 2048 * 65536 : 0);
+    w.total = w.stage + (hidden == 256 ? (size_t)2 * 2 * 4096 * 65536 : 0);
     return w;
 }
 inline size_t workspace_bytes_for(int64_t P, int hidden = 64) { return workspace_layout(P, hidden).total; }
