@@ -468,14 +468,19 @@ def test_metrics_async_reads_what_metrics_reads():
         m = a.metrics(with_episode_log="arrays")
         sync.append((m["loss"], m["grad_norm"], m["episodes"], m["mean_return"], sorted(zip(m["episode_log"]["step"].tolist(),
                      m["episode_log"]["env"].tolist(), m["episode_log"]["ret"].tolist(), m["episode_log"]["len"].tolist()))))
+    def consume(h):      # the record arrays are views of a pinned buffer that the next-but-one read reuses: copy them out
+        m = h.result()
+        m["episode_log"] = {k: v.copy() for k, v in m["episode_log"].items()}
+        return m
+
     got, pending = [], None
     for _ in range(6):
         b.update(12)
         h = b.metrics_async()
         if pending is not None:
-            got.append(pending.result())
+            got.append(consume(pending))
         pending = h
-    got.append(pending.result())
+    got.append(consume(pending))
     assert len(got) == 6
     for s, m in zip(sync, got):
         assert m["episodes_dropped"] == 0
