@@ -29,16 +29,20 @@ struct TailArgs {
     int ordinal;
 };
 
-// symmetric buffer: two generations (seq & 1) of the folded local gradient, then two generations of arrival flags
+// Symmetric buffer of one rank (push protocol): two generations (seq & 1) of [DRL_MAX_RANKS] gradient copies -- rank s WRITES its
+// folded slices into slot s of every rank's buffer -- followed by two generations of arrival flags [DRL_MAX_RANKS][FLAG_CTAS]
+// (one flag per source rank and CTA slice, holding the sequence number of the step that wrote the slice).
+constexpr int FLAG_CTAS = 160;
 struct CommLayout {
-    size_t xgrad[2], flags[2], total;
+    size_t xgrad[2], flags[2], rank_stride, total;
 };
 __host__ __device__ inline CommLayout comm_layout(int64_t P) {
     CommLayout c;
     const size_t g = ((size_t)P * 4 + 255) / 256 * 256;
-    c.xgrad[0] = 0; c.xgrad[1] = g;
-    c.flags[0] = 2 * g; c.flags[1] = 2 * g + 128;
-    c.total = 2 * g + 256;
+    c.rank_stride = g;
+    c.xgrad[0] = 0; c.xgrad[1] = (size_t)DRL_MAX_RANKS * g;
+    c.flags[0] = 2 * (size_t)DRL_MAX_RANKS * g; c.flags[1] = c.flags[0] + sizeof(uint32_t) * DRL_MAX_RANKS * FLAG_CTAS;
+    c.total = c.flags[1] + sizeof(uint32_t) * DRL_MAX_RANKS * FLAG_CTAS;
     return c;
 }
 

@@ -634,7 +634,6 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     const bool multi = tl.world > 1;
     const CommLayout cl = comm_layout(PP);
     const uint32_t gen = seq & 1u;
-    float* xg_local = multi ? reinterpret_cast<float*>(tl.peer[tl.rank] + cl.xgrad[gen]) : nullptr;
     double sq = 0.0;
     for (int p0 = p_lo; p0 < p_hi; p0 += 64) {
         const int p = p0 + pl;
@@ -671,7 +670,10 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
 #pragma unroll
             for (int y = 1; y < 8; ++y) t += tred[y * 64 + pl];
             if (multi) {
-                xg_local[p] = t;                                  // published to the peers below
+                // push: this rank's folded value goes into slot `rank` of EVERY rank's symmetric buffer (remote stores over NVLink
+                // are posted; nobody has to fetch it later)
+                for (int rk = 0; rk < tl.world; ++rk)
+                    reinterpret_cast<float*>(tl.peer[rk] + cl.xgrad[gen] + (size_t)tl.rank * cl.rank_stride)[p] = t;
             } else {
                 tl.grad_out[p] = t;
                 const double gs = (double)(t * ad.grad_scale);
@@ -682,15 +684,15 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     }
     TC_KSTAMP(7);
     if (multi) {
-        // ---- one-shot all-reduce over NVLink: publish, signal every peer, wait for every peer, sum in rank order ----
-        __threadfence_system();
-        grid_barrier(tl.ctr + 1);                 // this rank's whole gradient is in its symmetric buffer
-        if (blockIdx.x == 0 && tid < tl.world) {
-            __threadfence_system();
-            *reinterpret_cast<volatile uint32_t*>(tl.peer[tid] + cl.flags[gen] + 4 * tl.rank) = seq;
-        }
+        // ---- one-shot all-reduce over NVLink, slice by slice: every CTA publishes ITS slice with its own flag in every peer's
+        // buffer as soon as the slice is folded, and waits only for the same slice of the other ranks (no grid-wide barrier) ----
+        if (sl == 0) __threadfence_system();          // the threads that wrote: their remote stores are ordered before the flag
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
         if (tid < tl.world) {
-            const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(tl.peer[tl.rank] + cl.flags[gen] + 4 * tid);
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(tl.peer[tid] + cl.flags[gen] + sizeof(uint32_t) * (tl.rank * FLAG_CTAS + blockIdx.x)) = seq;
+            const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(tl.peer[tl.rank] + cl.flags[gen] +
+                                                                                    sizeof(uint32_t) * (tid * FLAG_CTAS + blockIdx.x));
             const long long t0 = clock64();
             while (*f < seq) {
                 if (clock64() - t0 > 40000000000ll) {   // ~20 s: a peer is gone (start-up skew between ranks can reach seconds)
@@ -701,10 +703,11 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             __threadfence_system();
         }
         named_bar_sync(BAR_TAIL, TC_COMPUTE);
+        const float* mine = reinterpret_cast<const float*>(tl.peer[tl.rank] + cl.xgrad[gen]);
         for (int p = p_lo + tid; p < p_hi; p += TC_COMPUTE) {
             float t = 0.0f;
-            for (int rk = 0; rk < tl.world; ++rk)
-                t += __ldcg(reinterpret_cast<const float*>(tl.peer[rk] + cl.xgrad[gen]) + p);
+            for (int rk = 0; rk < tl.world; ++rk)                      // rank order: the same sum on every rank
+                t += __ldcg(mine + (size_t)rk * (cl.rank_stride / sizeof(float)) + p);
             tl.grad_out[p] = t;
             const double gs = (double)(t * ad.grad_scale);
             sq = fma(gs, gs, sq);
