@@ -102,6 +102,18 @@ SIGNATURES = {
     "drl_comm_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "drl_comm_close": (C.c_int, [C.c_void_p]),
     "drl_comm_free": (C.c_int, [C.c_void_p]),
+    "drl_replay_sample_uniform": (C.c_int, [u32p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "drl_replay_gather": (C.c_int, [f32p, i32p, f32p, u8p, u32p, C.c_uint32, C.c_int32, f32p, f32p, i32p, f32p, u8p, C.c_void_p]),
+    "drl_replay_scratch_bytes": (C.c_size_t, [C.c_uint32]),
+    "drl_replay_sample_priority": (C.c_int, [f32p, C.c_uint32, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64, u32p, f32p, C.c_void_p,
+                                             C.c_size_t, C.c_void_p]),
+    "drl_replay_update_priorities": (C.c_int, [f32p, u32p, f32p, C.c_uint32, f32p, C.c_void_p]),
+    "drl_reinforce_param_count": (C.c_int, []),
+    "drl_reinforce_episodes": (C.c_int, [C.POINTER(EnvT), f32p, C.c_int32, C.c_uint64, f32p, u8p, f32p, u8p, i32p, u32p, C.POINTER(EpLogT),
+                                         C.c_void_p]),
+    "drl_reinforce_grad": (C.c_int, [f32p, f32p, u8p, f32p, i32p, u32p, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_float, f32p, f32p,
+                                     f32p, f32p, C.c_void_p]),
+    "drl_adam_step": (C.c_int, [f32p, f32p, f32p, f32p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "drl_selftest_umma": (C.c_int, [C.c_int32, C.c_int32, f32p, f32p, f32p, C.c_void_p]),
     "drl_selftest_tanh": (C.c_int, [f32p, f32p, C.c_int64, C.c_void_p]),
     "drl_clip_adam": (C.c_int, [C.POINTER(NetT), f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_double,

@@ -240,6 +240,46 @@ int drl_clip_adam(const drl_net_t* net, float* params, const float* grad, float*
                   int64_t step, double lr, double beta1, double beta2, double eps, double max_grad_norm,
                   double grad_scale, float* packed_out, float* norm_out, void* stream);
 
+/* ---- replay-buffer sampling and gather: the random-index gather family of the off-policy scripts ----
+ * Storage is flat struct-of-arrays with the reference's one-slot shift (dqn.py:74-77,104-109): obs [cap+1][OP] (padded rows),
+ * act [cap+1] int32, rew [cap+1], term [cap+1] u8; transition i = (obs[i], act[i], rew[i+1], term[i+1], obs[i+1]).
+ * Index draws use the build's Philox stream (word 0 of philox(i, draw_ctr, TAG_REPLAY)), not numpy's / torch's MT19937. */
+/* batch_inds = np.random.randint(size, size=batch)                                           dqn.py:116 */
+int drl_replay_sample_uniform(uint32_t* idx_out, uint32_t batch, uint32_t size, uint64_t seed, uint64_t draw_ctr, void* stream);
+/* b_observations, b_actions, b_next_observations, b_rewards, b_terminated of one batch      dqn.py:118-122, per.py:131-135 */
+int drl_replay_gather(const float* obs, const int32_t* act, const float* rew, const uint8_t* term, const uint32_t* idx, uint32_t batch,
+                      int32_t obs_stride, float* b_obs, float* b_next_obs, int32_t* b_act, float* b_rew, uint8_t* b_term, void* stream);
+/* batch_inds = torch.multinomial(priorities, batch, replacement=True) and b_probabilities = p^alpha / sum(p^alpha) at those
+ * indices (prob_out nullable)                                                                per.py:127-131 */
+size_t drl_replay_scratch_bytes(uint32_t size);
+int drl_replay_sample_priority(const float* priorities, uint32_t size, float alpha, uint32_t batch, uint64_t seed, uint64_t draw_ctr,
+                               uint32_t* idx_out, float* prob_out, void* scratch, size_t scratch_bytes, void* stream);
+/* priorities[batch_inds] = |td_errors| (last duplicate wins); max_priority = max(max_priority, written values)   per.py:144-146 */
+int drl_replay_update_priorities(float* priorities, const uint32_t* idx, const float* td_errors, uint32_t batch, float* max_priority_inout,
+                                 void* stream);
+
+/* ---- REINFORCE on the device-resident CartPole (deep_rl/reinforce.py:38-77) ----
+ * Policy = Sequential(Linear(4,128), Dropout(0.6), ReLU, Linear(128,2), Softmax); params flat in state_dict order
+ * (0.weight [128][4], 0.bias [128], 3.weight [2][128], 3.bias [2]) = drl_reinforce_param_count() floats.
+ * drl_reinforce_episodes: every env runs ONE episode (reset, then act / step until done, at most T = max_episode_steps
+ * steps; reinforce.py:55-67).  Planes [T+1][N] with the one-slot shift of the PPO buffers (rew[t+1], done[t+1] belong to
+ * act[t]); slots after the end of an episode hold reward 0 / done 1.  step0 >= 1 is the global step index of the first step
+ * (Philox counter); mask_bits_out (nullable, [T][N][4] words) receives the dropout keep mask of every step.
+ * Returns (reinforce.py:67) = drl_gae on these planes with gae_lambda = 1 and an all-zero value plane.
+ * drl_reinforce_grad: per-episode policy_loss = sum(-log_prob * (R - mean) / (std + exp(-5))) (reinforce.py:71-74) and its
+ * closed-form gradient, summed over the N episodes and multiplied by grad_scale; mask_bits NULL = regenerate the Philox dropout
+ * masks of (seed, env_gid0 + n, step0 + t), else use the given ones (teacher forcing).  grad_part [N][P], loss_part [N] scratch.
+ * drl_adam_step: torch.optim.Adam on a flat vector (reinforce.py:45,77; no clipping), `step` 1-based. */
+int drl_reinforce_param_count(void);
+int drl_reinforce_episodes(const drl_env_t* env, const float* params, int32_t T, uint64_t step0, float* obs /*[T+1][N][4]*/,
+                           uint8_t* act, float* rew, uint8_t* done, int32_t* ep_len /*[N]*/, uint32_t* mask_bits_out,
+                           const drl_ep_log_t* log, void* stream);
+int drl_reinforce_grad(const float* params, const float* obs, const uint8_t* act, const float* returns, const int32_t* ep_len,
+                       const uint32_t* mask_bits, int32_t N, uint64_t seed, uint32_t env_gid0, uint64_t step0, float grad_scale,
+                       float* grad_out, float* loss_out, float* grad_part, float* loss_part, void* stream);
+int drl_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step, double lr, double beta1,
+                  double beta2, double eps, void* stream);
+
 /* ---- diagnostics: runs one tcgen05.mma operand-layout combination of the update kernel on caller matrices
  * (fp32 row-major in, fp32 row-major out; operands are rounded to bf16).  See csrc/umma_selftest.cu. ---- */
 int drl_selftest_umma(int32_t mode, int32_t variant, const float* a, const float* b, float* d_out, void* stream);

@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         L.drl_or_vec_reset.argtypes = [C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, f64p, i32p, f32p, i32p, f32p]
         L.drl_or_vec_obs.argtypes = [C.c_int32, C.c_int32, f64p, f32p]
         L.drl_or_gae.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_int32, C.c_int32, C.c_float, C.c_float]
+        L.drl_or_replay_uniform.argtypes = [u32p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64]
+        L.drl_or_replay_priority.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, u32p, f64p]
         _lib = L
     return _lib
 
@@ -185,3 +187,32 @@ class OracleVecEnv:
                               _p(fin_ret, C.c_float), _p(fin_len, C.c_int32), self.max_steps)
         self.step_count += 1
         return obs, rew, done, {"final_return": fin_ret, "final_length": fin_len}
+
+
+# ---- replay-buffer samplers and gather (deep_rl/dqn.py:116-122, deep_rl/per.py:127-146) ----
+def replay_uniform(batch: int, size: int, seed: int, draw_ctr: int) -> np.ndarray:
+    out = np.zeros(batch, dtype=np.uint32)
+    lib().drl_or_replay_uniform(_p(out, C.c_uint32), batch, size, seed, draw_ctr)
+    return out
+
+
+def replay_priority(priorities: np.ndarray, batch: int, seed: int, draw_ctr: int) -> np.ndarray:
+    pri = np.ascontiguousarray(priorities, dtype=np.float32)
+    out = np.zeros(batch, dtype=np.uint32)
+    scratch = np.zeros((len(pri) + 1023) // 1024 + 1, dtype=np.float64)
+    lib().drl_or_replay_priority(_p(pri, C.c_float), len(pri), batch, seed, draw_ctr, _p(out, C.c_uint32), _p(scratch, C.c_double))
+    return out
+
+
+def replay_gather(obs, act, rew, term, idx):
+    """The five gathers of dqn.py:118-122 with numpy fancy indexing (one-slot shift: reward / terminated / next obs at idx + 1)."""
+    i = np.asarray(idx, dtype=np.int64)
+    return obs[i], act[i], obs[i + 1], rew[i + 1], term[i + 1]
+
+
+def replay_probabilities(priorities: np.ndarray, idx, alpha: float) -> np.ndarray:
+    """per.py:128,131: (priorities ** alpha / sum(priorities ** alpha))[batch_inds], float32 like the reference."""
+    import torch
+    p = torch.as_tensor(np.asarray(priorities, dtype=np.float32))
+    prob = p ** alpha / torch.sum(p ** alpha)
+    return prob[torch.as_tensor(np.asarray(idx, dtype=np.int64))].numpy()

@@ -33,6 +33,14 @@ class _Discrete:
         self.n = int(n)
         self.shape = ()
         self.dtype = np.int64
+        self._rng = np.random.RandomState()
+
+    def seed(self, seed=None):            # gym.spaces.Space.seed / .sample (dqn.py:67,94)
+        self._rng = np.random.RandomState(seed)
+        return [seed]
+
+    def sample(self):
+        return int(self._rng.randint(self.n))
 
 
 class Env:
@@ -140,8 +148,15 @@ class _TimeLimit(Wrapper):
 _REGISTRY = {"CartPole-v1": 500, "Acrobot-v1": 500}
 
 
+class _Spec:
+    def __init__(self, env_id, max_episode_steps):
+        self.id, self.max_episode_steps = env_id, max_episode_steps
+
+
 def make(env_id):
-    return _TimeLimit(_ClassicControl(env_id), _REGISTRY[env_id])
+    env = _TimeLimit(_ClassicControl(env_id), _REGISTRY[env_id])
+    env.spec = _Spec(env_id, _REGISTRY[env_id])      # env.spec.max_episode_steps (reinforce.py:53-54)
+    return env
 
 
 from . import wrappers  # noqa: E402,F401
