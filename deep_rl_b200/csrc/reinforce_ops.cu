@@ -18,6 +18,7 @@ drl_ep_log_t log_or_empty(const drl_ep_log_t* log);
 
 constexpr int RH = 128;                 // hidden width
 constexpr int RP = 4 * RH + RH + 2 * RH + 2;      // 898 parameters: 0.weight [128][4], 0.bias [128], 3.weight [2][128], 3.bias [2]
+constexpr int RPP = (RP + 3) / 4 * 4;   // row stride of the per-episode gradient scratch (16-byte aligned rows)
 constexpr uint32_t TAG_DROPOUT = 4;
 constexpr float KEEP = 0.4f, DSCALE = 2.5f;        // Dropout(p = 0.6): keep with probability 0.4, scale by 1 / 0.4
 
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(128) reinforce_episode_kernel(drl_env_t env, c
 
 // Per-environment gradient of policy_loss = sum_t -log_prob_t * (R_t - mean) / (std + exp(-5)) over the episode's steps
 // (reinforce.py:71-74), closed form: dlogit_a' = -Rhat_t (1[a' = a_t] - p_a'), back through Linear / ReLU / Dropout / Linear.
-// returns = the discounted reward-to-go plane of drl_gae(lambda = 1, V = 0).  Output: grad_part [N][RP], loss_part [N].
+// returns = the discounted reward-to-go plane of drl_gae(lambda = 1, V = 0).  Output: grad_part [N][RPP] (rows padded to a multiple of 4 floats), loss_part [N].
 __global__ void __launch_bounds__(128) reinforce_grad_kernel(const float* __restrict__ params, const float* __restrict__ obs,
                                                              const uint8_t* __restrict__ act, const float* __restrict__ returns,
                                                              const int32_t* __restrict__ ep_len, const uint32_t* __restrict__ mask_bits,
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(128) reinforce_grad_kernel(const float* __rest
             for (int i = 0; i < 4; ++i) gw1[j][i] = fmaf(dz, x[i], gw1[j][i]);
         }
     }
-    float* g = grad_part + (size_t)n * RP;
+    float* g = grad_part + (size_t)n * RPP;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         *reinterpret_cast<float4*>(g + (4 * lane + j) * 4) = make_float4(gw1[j][0], gw1[j][1], gw1[j][2], gw1[j][3]);
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(256) reinforce_fold_kernel(const float* __rest
     const bool is_loss = p == RP;
     float a = 0.0f;
     if (p <= RP)
-        for (int n = threadIdx.y; n < N; n += 8) a += is_loss ? loss_part[n] : grad_part[(size_t)n * RP + p];
+        for (int n = threadIdx.y; n < N; n += 8) a += is_loss ? loss_part[n] : grad_part[(size_t)n * RPP + p];
     sh[threadIdx.y][threadIdx.x] = a;
     __syncthreads();
     if (threadIdx.y == 0 && p <= RP) {

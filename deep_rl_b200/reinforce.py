@@ -76,7 +76,7 @@ class ReinforceTrainer:
         self.exp_avg = torch.zeros(P, dtype=f32, device=d)
         self.exp_avg_sq = torch.zeros(P, dtype=f32, device=d)
         self.loss = torch.zeros(1, dtype=f32, device=d)
-        self._grad_part = torch.zeros((N, P), dtype=f32, device=d)
+        self._grad_part = torch.zeros((N, (P + 3) // 4 * 4), dtype=f32, device=d)     # rows padded to 16 bytes
         self._loss_part = torch.zeros(N, dtype=f32, device=d)
         self.net = _lib.NetT(4, 64, 2, 4)              # shape argument of drl_gae (plane strides only)
         self.buf = _lib.RolloutBufT(0, 0, 0, self.zeros.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(), 0)

@@ -268,7 +268,7 @@ int drl_replay_update_priorities(float* priorities, const uint32_t* idx, const f
  * Returns (reinforce.py:67) = drl_gae on these planes with gae_lambda = 1 and an all-zero value plane.
  * drl_reinforce_grad: per-episode policy_loss = sum(-log_prob * (R - mean) / (std + exp(-5))) (reinforce.py:71-74) and its
  * closed-form gradient, summed over the N episodes and multiplied by grad_scale; mask_bits NULL = regenerate the Philox dropout
- * masks of (seed, env_gid0 + n, step0 + t), else use the given ones (teacher forcing).  grad_part [N][P], loss_part [N] scratch.
+ * masks of (seed, env_gid0 + n, step0 + t), else use the given ones (teacher forcing).  Scratch: grad_part [N][(P + 3) / 4 * 4], loss_part [N].
  * drl_adam_step: torch.optim.Adam on a flat vector (reinforce.py:45,77; no clipping), `step` 1-based. */
 int drl_reinforce_param_count(void);
 int drl_reinforce_episodes(const drl_env_t* env, const float* params, int32_t T, uint64_t step0, float* obs /*[T+1][N][4]*/,
