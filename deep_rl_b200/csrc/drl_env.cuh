@@ -139,14 +139,31 @@ __device__ __forceinline__ void env_reset_state(double (&s)[4], uint64_t seed, u
     s[3] = -half + (2.0 * half) * u01_f64(o.w);
 }
 
+// The physics of one step for a given action (no wrappers): new state in s, reward out, returns terminated.  Depends on the state
+// and the action only, so it can be evaluated for every possible action before the action is known (rollout_tc.cu).
+template <int KIND>
+__device__ __forceinline__ bool env_physics(double (&s)[4], int action, float& reward) {
+    if constexpr (KIND == DRL_ENV_CARTPOLE) { reward = 1.0f; return cartpole_physics(s, action); }
+    else if constexpr (KIND == DRL_ENV_MOUNTAINCAR) { reward = -1.0f; return mountaincar_physics(s, action); }
+    else { return acrobot_physics(s, action, reward); }
+}
+
 // One env step with TimeLimit, episode statistics and auto-reset.  Returns done; `reward` out.
+template <int KIND>
+__device__ __forceinline__ bool env_after_physics(EnvLane& e, bool term, float reward, uint64_t seed, uint32_t gid, uint64_t step,
+                                                  int max_episode_steps, const drl_ep_log_t& log);
+
 template <int KIND>
 __device__ __forceinline__ bool env_step(EnvLane& e, int action, float& reward, uint64_t seed, uint32_t gid,
                                          uint64_t step, int max_episode_steps, const drl_ep_log_t& log) {
-    bool term;
-    if constexpr (KIND == DRL_ENV_CARTPOLE) { term = cartpole_physics(e.s, action); reward = 1.0f; }
-    else if constexpr (KIND == DRL_ENV_MOUNTAINCAR) { term = mountaincar_physics(e.s, action); reward = -1.0f; }
-    else { term = acrobot_physics(e.s, action, reward); }
+    const bool term = env_physics<KIND>(e.s, action, reward);
+    return env_after_physics<KIND>(e, term, reward, seed, gid, step, max_episode_steps, log);
+}
+
+// TimeLimit (done = terminated or elapsed >= max), RecordEpisodeStatistics, finished-episode log and auto-reset, after the physics
+template <int KIND>
+__device__ __forceinline__ bool env_after_physics(EnvLane& e, bool term, float reward, uint64_t seed, uint32_t gid, uint64_t step,
+                                                  int max_episode_steps, const drl_ep_log_t& log) {
     e.elapsed += 1;
     bool done = term || (e.elapsed >= max_episode_steps);
     e.ep_ret = e.ep_ret + reward;

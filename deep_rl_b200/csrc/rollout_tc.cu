@@ -15,8 +15,11 @@
 //   S1  all: layer 1 on CUDA cores for 32/REP units -> bf16 SW128 tile (all REP rows of the env); hand the forward GEMM
 //   S2  all: wait, tcgen05.ld z2, tanh, partial head dot products -> exchange buffer
 //   --  group barrier
-//   S3  owners: logits / value, value store, Philox inverse-CDF sample, log-prob, fp64 env step with auto-reset
-//       and episode statistics, reward / done stores
+//   ENV  four extra warps (one per 32 env rows, lane = env): the fp64 physics of the step for EVERY action, from the state the
+//       owner published in S0 -- the physics depends on (state, action) only, so the candidates are computed while the compute
+//       warps run the MLP (S1, GEMM, S2) instead of after the sample
+//   S3  owners: logits / value, value store, Philox inverse-CDF sample, log-prob, pick the candidate of the sampled action,
+//       TimeLimit / episode statistics / auto-reset, reward / done stores
 #include "drl_env.cuh"
 #include "drl_pack.cuh"
 #include "drl_tc_common.cuh"
@@ -33,7 +36,7 @@ __device__ long long g_ro_dbg[1024];
 #else
 #define RO_STAMP(ev) do { } while (0)
 #endif
-enum : uint32_t { RB_FWD = 1, RB_ROW0 = 2 };   // named barriers: issuer hand-off, 4 row-window barriers (2..5)
+enum : uint32_t { RB_FWD = 1, RB_ROW0 = 2, RB_ROW1 = 6 };   // named barriers: issuer hand-off; per row group: state published (2..5), step evaluated (6..9)
 
 template <int O, int A>
 struct RoTcSmem {
@@ -43,12 +46,17 @@ struct RoTcSmem {
     static constexpr int OFF_H1 = (OFF_W + W_BYTES + 1023) / 1024 * 1024;   // (actor, critic) x 16 KB
     static constexpr int OFF_OBS = OFF_H1 + 32768;                           // fp32 [128][OW]
     static constexpr int OFF_XCH = OFF_OBS + TC_TILE * P::OW * 4;            // fp32 [32 slots][128] head partial sums
-    static constexpr int OFF_BAR = OFF_XCH + 32 * TC_TILE * 4;
+    static constexpr int OFF_ST = OFF_XCH + 32 * TC_TILE * 4;                // published env state: double [128][4]
+    static constexpr int OFF_CAND = OFF_ST + TC_TILE * 32;                   // candidates: double [3 actions][128][4] + {reward, term} [3][128]
+    static constexpr int OFF_BAR = OFF_CAND + 3 * TC_TILE * 32 + 3 * TC_TILE * 8;
     static constexpr int TOTAL = OFF_BAR + 64 + 1024;
 };
 
+constexpr int RO_ENV_WARPS = 4;
+constexpr int RO_THREADS = TC_THREADS + 32 * RO_ENV_WARPS;
+
 template <int KIND, int REP>
-__global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env, const float* __restrict__ packed, int T,
+__global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(drl_env_t env, const float* __restrict__ packed, int T,
                                                                    uint64_t step0, drl_rollout_buf_t buf, drl_ep_log_t log, const drl_ctrl_t* __restrict__ ctrl) {
     if (ctrl != nullptr) step0 = ctrl->env_step;      // graph-replayable launch: the counter lives in device memory
     using SP = EnvSpec<KIND>;
@@ -59,6 +67,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
     constexpr int ROWS = TC_TILE / REP;       // environments per CTA
     constexpr int QG = 4 / REP;               // lane quadrants per replica
     constexpr int UPT = HU / REP;             // hidden units per thread
+    // Candidate physics for every action on the env warps pays when the physics is short next to the MLP (CartPole's Euler step,
+    // MountainCar): Acrobot's RK4 step costs about as much as the whole MLP pass, three of them per env would become the
+    // critical path, so there the owner evaluates the sampled action only.
+    constexpr bool SPECULATE = KIND != DRL_ENV_ACROBOT;
     static_assert(OW == OP, "obs stride");
     static_assert(REP == 1 || REP == 2 || REP == 4, "replication factor");
     extern __shared__ unsigned char smem_raw[];
@@ -72,6 +84,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
     unsigned char* tH1 = sm + S::OFF_H1;
     float* obs_s = reinterpret_cast<float*>(sm + S::OFF_OBS);
     float* xch = reinterpret_cast<float*>(sm + S::OFF_XCH);
+    double* st_s = reinterpret_cast<double*>(sm + S::OFF_ST);
+    double* cand_s = reinterpret_cast<double*>(sm + S::OFF_CAND);
+    float2* cand_rt = reinterpret_cast<float2*>(sm + S::OFF_CAND + 3 * TC_TILE * 32);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd
     uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
 
@@ -121,6 +136,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
         return;
     }
 
+    if (warp > TC_COMPUTE / 32) {
+        // =========================== env warps: warp e <-> env rows 32e .. 32e+31 (row group e) ===========================
+        const int eg = warp - TC_COMPUTE / 32 - 1;
+        if (eg < ROWS / 32) {
+            const int er_e = eg * 32 + lane;
+            const bool live = blockIdx.x * ROWS + er_e < env.num_envs;
+            for (int t = 0; t <= T; ++t) {
+                named_bar_sync(RB_ROW0 + eg, 128 * REP + 32);            // the owners have published the state of step t
+                if (SPECULATE && t < T && live) {
+                    const double2* sp = reinterpret_cast<const double2*>(st_s + er_e * 4);
+                    const double2 s01 = sp[0], s23 = sp[1];
+#pragma unroll
+                    for (int a = 0; a < A; ++a) {
+                        double cs[4] = {s01.x, s01.y, s23.x, s23.y};
+                        float creward;
+                        const bool cterm = env_physics<KIND>(cs, a, creward);
+                        double2* cp = reinterpret_cast<double2*>(cand_s + ((size_t)a * TC_TILE + er_e) * 4);
+                        cp[0] = make_double2(cs[0], cs[1]);
+                        cp[1] = make_double2(cs[2], cs[3]);
+                        cand_rt[a * TC_TILE + er_e] = make_float2(creward, cterm ? 1.0f : 0.0f);
+                    }
+                }
+                named_bar_arrive(RB_ROW1 + eg, 128 * REP + 32);          // candidates ready (the owners sync on this after S2)
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        return;
+    }
+
     // =========================== compute warps ===========================
     const int q = warp & 3, half = (warp >> 2) & 1, net = (warp >> 3) & 1;
     const int grp = q % QG, replica = q / QG;
@@ -153,6 +198,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
                 float4* o4 = reinterpret_cast<float4*>(buf.obs + ((size_t)t * N + n) * OP);
 #pragma unroll
                 for (int qq = 0; qq < OP / 4; ++qq) o4[qq] = make_float4(obs[4 * qq], obs[4 * qq + 1], obs[4 * qq + 2], obs[4 * qq + 3]);
+                double2* sp = reinterpret_cast<double2*>(st_s + er * 4);        // for the env warps' candidate steps
+                sp[0] = make_double2(e.s[0], e.s[1]);
+                sp[1] = make_double2(e.s[2], e.s[3]);
             }
             // layer-1 input as the update's GEMM sees it: obs = hi + lo with both halves rounded to bf16 (update_tc.cu loader)
 #pragma unroll
@@ -165,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
                 *reinterpret_cast<float4*>(obs_s + er * OW + 4 * qq) = make_float4(obs[4 * qq], obs[4 * qq + 1], obs[4 * qq + 2], obs[4 * qq + 3]);
         }
         RO_STAMP(1);
-        named_bar_sync(RB_ROW0 + grp, 128 * REP);
+        named_bar_sync(RB_ROW0 + grp, 128 * REP + 32);
         RO_STAMP(2);
 
         // ---- S1: layer 1 (UPT units of this thread's net) -> bf16 tile rows of every replica, hand the forward GEMM ----
@@ -255,7 +303,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
         }
         RO_STAMP(6);
         umma::fence_before_sync();
-        named_bar_sync(RB_ROW0 + grp, 128 * REP);
+        named_bar_sync(RB_ROW1 + grp, 128 * REP + 32);
         RO_STAMP(7);
 
         // ---- S3: owners: value store, sample, env step ----
@@ -288,7 +336,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_tc_kernel(drl_env_t env
                 buf.act[i0] = (uint8_t)act;
                 buf.logp[i0] = lp;
                 float reward;
-                const bool done = env_step<KIND>(e, act, reward, env.seed, gid, step, env.max_episode_steps, log);
+                bool term;
+                if (SPECULATE) {          // the env warp has evaluated every action: take the sampled one
+                    const double2* cp = reinterpret_cast<const double2*>(cand_s + ((size_t)act * TC_TILE + er) * 4);
+                    const double2 c01 = cp[0], c23 = cp[1];
+                    e.s[0] = c01.x; e.s[1] = c01.y; e.s[2] = c23.x; e.s[3] = c23.y;
+                    const float2 rt = cand_rt[act * TC_TILE + er];
+                    reward = rt.x; term = rt.y != 0.0f;
+                } else {
+                    term = env_physics<KIND>(e.s, act, reward);
+                }
+                const bool done = env_after_physics<KIND>(e, term, reward, env.seed, gid, step, env.max_episode_steps, log);
                 buf.rew[i0 + N] = reward;
                 buf.done[i0 + N] = done ? 1 : 0;
                 RO_STAMP(11);
@@ -308,7 +366,7 @@ static int launch_rollout_tc_rep(const drl_env_t& env, const float* packed, int 
     DRL_CUDA(cudaFuncSetAttribute(rollout_tc_kernel<KIND, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     constexpr int ROWS = TC_TILE / REP;
     const int blocks = (env.num_envs + ROWS - 1) / ROWS;
-    rollout_tc_kernel<KIND, REP><<<blocks, TC_THREADS, smem, st>>>(env, packed, T, step0, buf, log, ctrl);
+    rollout_tc_kernel<KIND, REP><<<blocks, RO_THREADS, smem, st>>>(env, packed, T, step0, buf, log, ctrl);
     DRL_LAUNCH_CHECK("rollout_tc_kernel");
     return DRL_OK;
 }
