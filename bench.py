@@ -368,7 +368,8 @@ def _run_config(name, env_id, envs, T, hidden, steps, warm, rank, world, dev, fl
     rec = {"name": name, "workload": f"{env_id}, {envs} envs/GPU x {T} steps, {hidden}-wide MLP, {world} GPU(s)", "value": value,
            "unit": "env-steps/s", "ms_per_step": dev_ms / steps, "steps": steps, "warmup": warm, "n_gpus": world,
            "dtype": "bf16" if tc else "f32", "episodes_dropped": m["episodes_dropped"],
-           "roofline": _grad_roofline(env_id, hidden, cfg.minibatch_size, phases, local_ms, value, world, tc, peaks),
+           "roofline": _grad_roofline(env_id, hidden, cfg.minibatch_size * tr.mb_per_launch, phases, local_ms, value, world, tc, peaks),
+           "minibatches_per_launch": tr.mb_per_launch,
            "rooflines": _hbm_rooflines(env_id, envs, T, cfg.update_epochs, phases, peaks),
            "phases_ms_per_update": {k: v["total_ms"] / inst_steps for k, v in phases.items()}, "gpu_launches": launches,
            "cuda_graph": tr._graph is not None}
@@ -531,9 +532,14 @@ def run_b200(args):
             traffic = json.load(open(tpath)).get(f"{'ppo_grad_tc_kernel' if tc else 'ppo_grad_kernel'}@{M}")
         except Exception:
             traffic = None
-    roofline = _grad_roofline(args.env_id, hidden, M, phases, local_ms, value, world, tc, peaks, traffic)
+    mb_per_launch = tr.mb_per_launch
+    if traffic is not None:
+        traffic = traffic * mb_per_launch
+    roofline = _grad_roofline(args.env_id, hidden, M * mb_per_launch, phases, local_ms, value, world, tc, peaks, traffic)
     roofline.update({
-        "kernel_launch_includes": "gradient + fold of the per-SM partials + clip + Adam (one cooperative launch)" if tc else "gradient kernel only",
+        "minibatches_per_launch": mb_per_launch,
+        "kernel_launch_includes": (f"{mb_per_launch} consecutive minibatch steps (one epoch), each = gradient + fold of the per-SM partials + clip + Adam, "
+                                   "in ONE cooperative launch") if tc else "gradient kernel only",
         "limiter": ("no single pipe: per 128-sample tile a MUFU-bound tanh section, an issue-bound FMA section and three ~600-cycle "
                     "tcgen05 round trips run back to back (one tile in flight per SM); the small GEMM instructions are bound by "
                     "operand fetch from shared memory, not math (DESIGN.md section 3, profiles/tools/mma_timing.cu)" if tc else "FP32 FMA issue"),

@@ -81,11 +81,11 @@ SIGNATURES = {
                                          C.POINTER(PpoCoefT), f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
     "drl_ppo_minibatch_update": (C.c_int, [C.POINTER(NetT), f32p, f32p, u32p, C.c_uint32, C.c_uint32, f32p, C.POINTER(PpoCoefT),
                                            f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
-                                           C.c_double, f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
+                                           C.c_double, f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int32, C.c_void_p]),
     "drl_ppo_minibatch_update_dist": (C.c_int, [C.POINTER(NetT), f32p, f32p, u32p, C.c_uint32, C.c_uint32, f32p, C.POINTER(PpoCoefT),
                                                 f32p, f32p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                                 C.c_double, f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(CommT),
-                                                C.c_void_p]),
+                                                C.c_int32, C.c_void_p]),
     "drl_ctrl_set": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double,
                                C.c_void_p]),
     "drl_rollout_ctl": (C.c_int, [C.POINTER(EnvT), C.POINTER(NetT), f32p, C.c_int32, C.c_void_p, C.POINTER(RolloutBufT),
@@ -96,7 +96,7 @@ SIGNATURES = {
     "drl_ppo_minibatch_update_ctl": (C.c_int, [C.POINTER(NetT), f32p, f32p, u32p, C.c_uint32, C.c_uint32, f32p, C.POINTER(PpoCoefT),
                                                f32p, f32p, f32p, f32p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double,
                                                C.c_double, f32p, f32p, C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(CommT),
-                                               C.c_void_p]),
+                                               C.c_int32, C.c_void_p]),
     "drl_comm_bytes": (C.c_size_t, [C.POINTER(NetT)]),
     "drl_comm_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     "drl_comm_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -5,6 +5,8 @@
 
 namespace drl {
 
+constexpr int DRL_MAX_STEPS_PER_LAUNCH = 8;
+
 struct AdamArgs {
     float* params; const float* grad; float* m; float* v; float* packed; float* norm_out;
     int P;
@@ -27,6 +29,10 @@ struct TailArgs {
     // graph-replayable launch (drl_ppo_minibatch_update_ctl): Adam scalars and sequence number come from device memory
     const drl_ctrl_t* ctrl;
     int ordinal;
+    // one launch = nsteps consecutive, equally sized minibatches (GradArgs.mb_start + s * mb_count, adv_stats[2s], loss terms
+    // row s, optimizer step s): by-value Adam scalars per step (ctrl == nullptr)
+    int nsteps;
+    float neg_step_size_s[DRL_MAX_STEPS_PER_LAUNCH], bc2_sqrt_s[DRL_MAX_STEPS_PER_LAUNCH];
 };
 
 // Symmetric buffer of one rank (push protocol): two generations (seq & 1) of [DRL_MAX_RANKS] gradient copies -- rank s WRITES its

@@ -606,7 +606,7 @@ static int run_grad(const drl_net_t* net, const float* packed, const float* rec,
     g.ppad = w.ppad;
     g.dbg = getenv("DRL_TC_DEBUG") ? reinterpret_cast<long long*>((char*)workspace + w.debug) : nullptr;
     g.tail.enabled = 0;
-    g.tail.ctrl = nullptr; g.tail.ordinal = 0;
+    g.tail.ctrl = nullptr; g.tail.ordinal = 0; g.tail.nsteps = 1;
     if (g_out) { *g_out = g; if (grid_out == nullptr) return DRL_OK; }   // arguments only
     if (net->hidden == 256) {
         DRL_REQUIRE(flags & DRL_GRAD_TENSOR_CORES, "minibatch gradient: hidden=256 exists on the tensor-core path only");
@@ -646,12 +646,18 @@ static int minibatch_update_impl(const drl_net_t* net, float* packed, const floa
                                  uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params, float* grad_out,
                                  float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
                                  double max_grad_norm, float* loss_terms_out, float* norm_out, void* workspace, size_t workspace_bytes,
-                                 uint32_t flags, const drl_comm_t* comm, void* stream, const drl_ctrl_t* ctrl = nullptr, int ordinal = 0) {
+                                 uint32_t flags, const drl_comm_t* comm, void* stream, const drl_ctrl_t* ctrl = nullptr, int ordinal = 0,
+                                 int num_steps = 1) {
     int rc = check_net(net);
     if (rc != DRL_OK) return rc;
     if (net->hidden != H) { set_error("drl_ppo_minibatch_update: hidden=%d has no fused step (use drl_ppo_minibatch_grad + drl_clip_adam)", net->hidden); return DRL_ERR_UNSUPPORTED; }
     DRL_REQUIRE(params && exp_avg && exp_avg_sq, "drl_ppo_minibatch_update: NULL pointer");
     DRL_REQUIRE(step >= 1, "drl_ppo_minibatch_update: step=%lld must be >= 1", (long long)step);
+    DRL_REQUIRE(num_steps >= 1 && num_steps <= DRL_MAX_STEPS_PER_LAUNCH, "drl_ppo_minibatch_update: num_steps=%d (1..%d)", num_steps,
+                DRL_MAX_STEPS_PER_LAUNCH);
+    DRL_REQUIRE(num_steps == 1 || (flags & DRL_GRAD_TENSOR_CORES), "drl_ppo_minibatch_update: num_steps > 1 needs the tensor-core path");
+    DRL_REQUIRE(ctrl == nullptr || ordinal + num_steps <= DRL_CTRL_MAX_STEPS, "drl_ppo_minibatch_update: ordinal %d + %d steps > %d", ordinal,
+                num_steps, DRL_CTRL_MAX_STEPS);
     cudaStream_t st = as_stream(stream);
     GradArgs g;
     int grid = 0;
@@ -670,6 +676,14 @@ static int minibatch_update_impl(const drl_net_t* net, float* packed, const floa
         g.tail.world = world; g.tail.rank = comm ? comm->rank : 0; g.tail.seq = comm ? comm->seq : 0;
         g.tail.error_flag = comm ? comm->error_flag : nullptr;
         g.tail.ctrl = ctrl; g.tail.ordinal = ordinal;
+        g.tail.nsteps = num_steps;
+        for (int sidx = 0; sidx < num_steps; ++sidx) {      // by-value Adam scalars of optimizer steps step .. step + num_steps - 1
+            AdamArgs tmp;
+            fill_adam(tmp, net, params, grad_out, exp_avg, exp_avg_sq, step + sidx, lr, beta1, beta2, eps, max_grad_norm, 1.0 / world, packed,
+                      norm_out);
+            g.tail.neg_step_size_s[sidx] = tmp.neg_step_size;
+            g.tail.bc2_sqrt_s[sidx] = tmp.bc2_sqrt;
+        }
         for (int r = 0; r < DRL_MAX_RANKS; ++r)
             g.tail.peer[r] = (comm && r < world) ? reinterpret_cast<unsigned char*>(comm->peer[r]) : nullptr;
         return launch_grad_tc_fused(net, g, st);
@@ -698,17 +712,18 @@ int drl_ppo_minibatch_update(const drl_net_t* net, float* packed, const float* r
                              uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params, float* grad_out,
                              float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
                              double max_grad_norm, float* loss_terms_out, float* norm_out, void* workspace, size_t workspace_bytes,
-                             uint32_t flags, void* stream) {
+                             uint32_t flags, int32_t num_steps, void* stream) {
     return minibatch_update_impl(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, params, grad_out, exp_avg, exp_avg_sq, step,
                                  lr, beta1, beta2, eps, max_grad_norm, loss_terms_out, norm_out, workspace, workspace_bytes, flags,
-                                 nullptr, stream);
+                                 nullptr, stream, nullptr, 0, num_steps);
 }
 
 int drl_ppo_minibatch_update_dist(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
                                   uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params,
                                   float* grad_out, float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1,
                                   double beta2, double eps, double max_grad_norm, float* loss_terms_out, float* norm_out,
-                                  void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm, void* stream) {
+                                  void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm, int32_t num_steps,
+                                  void* stream) {
     DRL_REQUIRE(comm != nullptr, "drl_ppo_minibatch_update_dist: comm is NULL");
     DRL_REQUIRE(comm->world >= 1 && comm->world <= DRL_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world,
                 "drl_ppo_minibatch_update_dist: world=%d rank=%d", comm->world, comm->rank);
@@ -716,7 +731,7 @@ int drl_ppo_minibatch_update_dist(const drl_net_t* net, float* packed, const flo
     for (int r = 0; r < comm->world; ++r) DRL_REQUIRE(comm->peer[r] != nullptr, "drl_ppo_minibatch_update_dist: peer[%d] is NULL", r);
     return minibatch_update_impl(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, params, grad_out, exp_avg, exp_avg_sq, step,
                                  lr, beta1, beta2, eps, max_grad_norm, loss_terms_out, norm_out, workspace, workspace_bytes, flags,
-                                 comm, stream);
+                                 comm, stream, nullptr, 0, num_steps);
 }
 
 int drl_ppo_minibatch_update_ctl(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
@@ -724,7 +739,7 @@ int drl_ppo_minibatch_update_ctl(const drl_net_t* net, float* packed, const floa
                                  float* grad_out, float* exp_avg, float* exp_avg_sq, const drl_ctrl_t* ctrl, int32_t ordinal,
                                  double beta1, double beta2, double eps, double max_grad_norm, float* loss_terms_out,
                                  float* norm_out, void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm,
-                                 void* stream) {
+                                 int32_t num_steps, void* stream) {
     DRL_REQUIRE(ctrl != nullptr, "drl_ppo_minibatch_update_ctl: ctrl is NULL");
     DRL_REQUIRE(ordinal >= 0 && ordinal < DRL_CTRL_MAX_STEPS, "drl_ppo_minibatch_update_ctl: ordinal=%d", ordinal);
     DRL_REQUIRE(flags & DRL_GRAD_TENSOR_CORES, "drl_ppo_minibatch_update_ctl: tensor-core path only");
@@ -736,7 +751,7 @@ int drl_ppo_minibatch_update_ctl(const drl_net_t* net, float* packed, const floa
     // step = 1 / lr = 0 only feed the by-value Adam scalars, which the kernel replaces with ctrl's
     return minibatch_update_impl(net, packed, rec, idx, mb_start, mb_count, adv_stats, coef, params, grad_out, exp_avg, exp_avg_sq, 1,
                                  0.0, beta1, beta2, eps, max_grad_norm, loss_terms_out, norm_out, workspace, workspace_bytes, flags,
-                                 comm, stream, ctrl, ordinal);
+                                 comm, stream, ctrl, ordinal, num_steps);
 }
 
 __global__ void ctrl_set_kernel(drl_ctrl_t* dst, drl_ctrl_t v) {

@@ -67,10 +67,10 @@ constexpr int GRAD_TC_BLOCK = TC_THREADS + 32;   // + the loader warp
 constexpr int RING = 3;                          // depth of the [obs|1] / scalar ring
 
 // sample id of row r of this CTA's tile `tile` (0xFFFFFFFF = padding row)
-__device__ __forceinline__ uint32_t tc_sample_index(const GradArgs& g, uint32_t tile, uint32_t ntiles, int r) {
+__device__ __forceinline__ uint32_t tc_sample_index(const GradArgs& g, uint32_t mb_start, uint32_t mb_count, uint32_t tile, uint32_t ntiles, int r) {
     const uint32_t pos = tile * TC_TILE + (uint32_t)r;
-    if (tile >= ntiles || pos >= g.mb_count) return 0xFFFFFFFFu;
-    const uint32_t i = g.mb_start + pos;
+    if (tile >= ntiles || pos >= mb_count) return 0xFFFFFFFFu;
+    const uint32_t i = mb_start + pos;
     return g.idx ? __ldg(g.idx + i) : i;
 }
 
@@ -108,8 +108,11 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     const int rw = warp & 3, half = (warp >> 2) & 1, net = (warp >> 3) & 1;
     const int r = rw * 32 + lane;
     const int u0 = half * HU;
+    // One launch covers `nsteps` consecutive, equally sized minibatches (1 unless the fused tail is on): minibatch s starts at
+    // mb_start + s * mb_count; every CTA has nmy >= 1 tiles in each of them (the launchers guarantee grid <= ntiles).
+    const uint32_t nsteps = g.tail.enabled ? (uint32_t)g.tail.nsteps : 1u;
     const uint32_t ntiles = (g.mb_count + TC_TILE - 1) / TC_TILE;
-    const uint32_t nmy = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles of this CTA (>= 1)
+    const uint32_t nmy = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles of this CTA per minibatch (>= 1)
 
     // ---- prologue: barriers, TMEM, weights by TMA bulk copy ----
     TC_KSTAMP(0);
@@ -139,9 +142,12 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         // lane l owns rows l, l+32, l+64, l+96 of every tile.  Indices are fetched one tile ahead of the records.
         uint32_t sidx[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) sidx[q] = tc_sample_index(g, blockIdx.x, ntiles, lane + 32 * q);
+        for (int q = 0; q < 4; ++q) sidx[q] = tc_sample_index(g, g.mb_start, g.mb_count, blockIdx.x, ntiles, lane + 32 * q);
         uint32_t b = 0, use_par = 0;
-        for (uint32_t j = 0; j < nmy; ++j) {
+        // the gather does not depend on the weights: the loader runs straight through all minibatches of the launch, so the
+        // first tiles of minibatch s + 1 are in the ring while the fold / clip / Adam tail of minibatch s is still running
+        for (uint32_t jg = 0; jg < nsteps * nmy; ++jg) {
+            const uint32_t j = jg % nmy;
             float4 rv[4][OP / 4 + 1];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -155,11 +161,14 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
                     rv[q][OP / 4] = __ldg(r4 + RW / 4 - 1);
                 }
             }
-            if (j + 1 < nmy) {
+            if (jg + 1 < nsteps * nmy) {
+                const uint32_t jn = (jg + 1) % nmy, sn = (jg + 1) / nmy;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) sidx[q] = tc_sample_index(g, blockIdx.x + (j + 1) * gridDim.x, ntiles, lane + 32 * q);
+                for (int q = 0; q < 4; ++q)
+                    sidx[q] = tc_sample_index(g, g.mb_start + sn * g.mb_count, g.mb_count, blockIdx.x + jn * gridDim.x, ntiles, lane + 32 * q);
             }
-            if (j >= RING) mbar_wait(ring_empty + b, use_par ^ 1u);    // the GEMMs of tile j - RING have released the slot
+            (void)j;
+            if (jg >= RING) mbar_wait(ring_empty + b, use_par ^ 1u);   // the GEMMs of tile jg - RING have released the slot
             unsigned char* obst = tOBS + b * 4096;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             mbar_arrive(ring_full + b);
             if (++b == RING) { b = 0; use_par ^= 1u; }
         }
-        __syncthreads();           // epilogue barrier of the compute warps
+        __syncthreads();           // end of the kernel
         return;
     }
 
@@ -196,7 +205,6 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         constexpr uint32_t ID_DH1 = umma::make_idesc(128, 64, false, true);
         constexpr uint32_t ID_W2 = umma::make_idesc(128, 128, true, true);
         constexpr uint32_t ID_N16 = umma::make_idesc(128, 16, true, true);
-        mbar_wait(bars, 0);   // weight tiles have landed
         const uint32_t aW1B = smem_u32(tW1B);
         constexpr uint32_t ID_L1 = umma::make_idesc(128, 64, false, false);
         // layer 1 of tile k: z1 = [obs_hi|1|obs_lo] . [W1|b1|W1]^T, K = 16, both operands K-major without swizzle
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             umma::commit(bars + 4);
         };
         auto issue_fwd = [&](uint32_t k) {
-            const uint32_t h1b = aH1 + (k & 1u) * 32768;
+            const uint32_t h1b = aH1 + (k & 1u) * 32768;      // k = running tile number of the launch
 #pragma unroll
             for (int n2 = 0; n2 < 2; ++n2)
 #pragma unroll
@@ -220,6 +228,9 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         };
         uint32_t bn = 0, bn_par = 0;      // ring slot / use parity of the NEXT tile to get its layer-1 GEMM
         uint32_t bc = 0;                  // ring slot of the current tile
+        for (uint32_t s = 0; s < nsteps; ++s) {
+        const uint32_t kbase = s * nmy;
+        mbar_wait(bars, s & 1u);   // the weight tiles of this minibatch have landed
         named_bar_sync(BAR_L1, TC_THREADS);
         mbar_wait(ring_full + bn, bn_par);
         umma::fence_after_sync();
@@ -228,10 +239,10 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         if (++bn == RING) { bn = 0; bn_par ^= 1u; }
         named_bar_sync(BAR_FWD, TC_THREADS);
         umma::fence_after_sync();
-        if (umma::elect_one()) issue_fwd(0);
+        if (umma::elect_one()) issue_fwd(kbase);
         __syncwarp();
         for (uint32_t k = 0; k < nmy; ++k) {
-            const uint32_t par = k & 1u, acc = k > 0 ? 1u : 0u;
+            const uint32_t par = (kbase + k) & 1u, acc = k > 0 ? 1u : 0u;
             const uint32_t obsb = aOBS + bc * 4096;
             if (k + 1 < nmy) {
                 named_bar_sync(BAR_L1, TC_THREADS);      // z2(k) consumed
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
                 named_bar_sync(BAR_FWD, TC_THREADS);
                 umma::fence_after_sync();
                 TC_STAMP(2);
-                if (umma::elect_one()) issue_fwd(k + 1);
+                if (umma::elect_one()) issue_fwd(kbase + k + 1);
                 __syncwarp();
                 TC_STAMP(3);
             }
@@ -300,26 +311,32 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             TC_STAMP(5);
             if (++bc == RING) bc = 0;
         }
+        }   // minibatches of the launch
         umma::fence_before_sync();
-        __syncthreads();           // epilogue barrier of the compute warps
+        __syncthreads();           // end of the kernel
         return;
     }
 
     // =========================== compute warps ===========================
     const uint32_t trow = tmem + ((uint32_t)(rw * 32) << 16);   // this thread's TMEM lane
-    const float adv_mean = g.adv_stats[0], adv_rstd = 1.0f / (g.adv_stats[1] + 1e-8f);
     const float inv_m = 1.0f / (float)g.mb_count;
     const int wrow0 = net == 0 ? 0 : A;          // first head row of this net in sW4 / sB4
     const int nheads = net == 0 ? A : 1;
+    uint32_t rb = 0, rb_par = 0;          // ring slot / use parity of the current tile (run on across the minibatches of the launch)
+
+    for (uint32_t s = 0; s < nsteps; ++s) {
+    const uint32_t kbase = s * nmy;              // running tile number of this minibatch's first tile: barrier phases and the h1
+                                                 // double buffer continue across the minibatches of the launch
+    const float adv_mean = g.adv_stats[2 * s], adv_rstd = 1.0f / (g.adv_stats[2 * s + 1] + 1e-8f);
     float lsum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // pg, v, entropy, kl, clipfrac partial sums (half-0 threads only)
     float gb4[4] = {0.f, 0.f, 0.f, 0.f};         // head-bias gradients: actor slots 0..A-1, critic slot 3
 
     TC_KSTAMP(1);
-    mbar_wait(bars, 0);
+    mbar_wait(bars, s & 1u);
     TC_KSTAMP(2);
 
     // layer-1 epilogue of tile k: z1 from TMEM -> tanh -> bf16 h1 tile (buffer k & 1), then hand fwd(k)
-    auto phase0 = [&](uint32_t k) {
+    auto phase0 = [&](uint32_t k) {      // k = running tile number
         mbar_wait(bars + 4, k & 1u);
         umma::fence_after_sync();
         float h[HU];
@@ -333,12 +350,11 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     };
 
     named_bar_arrive(BAR_L1, TC_THREADS);
-    phase0(0);
-    uint32_t rb = 0, rb_par = 0;          // ring slot / use parity of the current tile
+    phase0(kbase);
     TC_KSTAMP(3);
 
     for (uint32_t k = 0; k < nmy; ++k) {
-        const uint32_t par = k & 1u;
+        const uint32_t par = (kbase + k) & 1u;
 
         // ================= X(k): heads, loss, output gradients, dz2 =================
         TC_STAMP(0);
@@ -361,7 +377,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
                 h[4 * k4 + 2] = tanh_mufu(h[4 * k4 + 2] + bb.z);
                 h[4 * k4 + 3] = tanh_mufu(h[4 * k4 + 3] + bb.w);
             }
-            if (k > 0) mbar_wait(bars + 5, (k - 1) & 1u);   // dW4(k-1) has finished reading the h2 and dout tiles
+            if (k > 0) mbar_wait(bars + 5, par ^ 1u);   // dW4(k-1) has finished reading the h2 and dout tiles
             store_half_row_sw128(tH2 + net * 16384, r, half * 4, h);
 
             // head partial sums over this thread's 32 units, exchanged with the thread owning the other 32
@@ -482,7 +498,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             }
             TC_STAMP(4);
             TC_STAMP(5);
-            if (k > 0) mbar_wait(bars + 6, (k - 1) & 1u);   // dW2/db2(k-1) have finished reading the dz2 and h1(k-1) tiles
+            if (k > 0) mbar_wait(bars + 6, par ^ 1u);   // dW2/db2(k-1) have finished reading the dz2 and h1(k-1) tiles
             store_half_row_sw128(tDZ + net * 16384, r, half * 4, h);
         }
         umma::fence_proxy_async();
@@ -492,7 +508,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
 
         // ================= Y(k): layer 1 of the next tile, hand fwd(k+1) (hides bwd(k)) =================
         if (k + 1 < nmy) {
-            phase0(k + 1);
+            phase0(kbase + k + 1);
         }
 
         // ================= Z(k): dz1 = dh1 * (1 - h1^2) (hides fwd(k+1)) =================
@@ -505,7 +521,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             TC_STAMP(10);
             mbar_wait(bars + 2, par);
             TC_STAMP(11);
-            if (k > 0) mbar_wait(bars + 3, (k - 1) & 1u);   // w1(k-1) has finished reading tDZ1
+            if (k > 0) mbar_wait(bars + 3, par ^ 1u);   // w1(k-1) has finished reading tDZ1
             umma::fence_after_sync();
             TC_STAMP(8);
             float dh[HU];
@@ -531,9 +547,9 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         TC_STAMP(9);
         if (++rb == RING) { rb = 0; rb_par ^= 1u; }
     }
-    mbar_wait(bars + 3, (nmy - 1) & 1u);
-    mbar_wait(bars + 5, (nmy - 1) & 1u);
-    mbar_wait(bars + 6, (nmy - 1) & 1u);
+    mbar_wait(bars + 3, (kbase + nmy - 1) & 1u);
+    mbar_wait(bars + 5, (kbase + nmy - 1) & 1u);
+    mbar_wait(bars + 6, (kbase + nmy - 1) & 1u);
     umma::fence_after_sync();
     TC_KSTAMP(4);
 
@@ -578,7 +594,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         }
     }
     umma::fence_before_sync();
-    __syncthreads();
+    named_bar_sync(13, TC_COMPUTE);       // compute warps only: the issuer and the loader run on into the next minibatch
     if (tid < 9) {
         float sv = 0.0f;
 #pragma unroll
@@ -587,7 +603,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         else if (tid - 5 < A) stage[P::C_NET + A * H + (tid - 5)] = sv;              // actor head bias
         else if (tid == 8) stage[P::C_ACTOR + P::C_NET + H] = sv;                    // critic head bias
     }
-    named_bar_sync(13, TC_COMPUTE);       // only the compute warps are left
+    named_bar_sync(13, TC_COMPUTE);
     for (int i = tid; i < P::C_ALL; i += TC_COMPUTE) {
         const int nb = i >= P::C_ACTOR ? 1 : 0;
         const int w = i - nb * P::C_ACTOR - W2_OFF;    // index inside this net's W2 block, if 0 <= w < H*H
@@ -595,23 +611,23 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         if (w >= 0 && w < H * H) src = i - (w & 63) + ((w & 63) ^ ((w >> 6) & 31));
         part[i] = stage[src];
     }
-    if (warp == 1) umma::tmem_dealloc(tmem, TC_COLS);
     TC_KSTAMP(5);
-    if (!g.tail.enabled) return;
-
+    if (g.tail.enabled) {
     // ================= in-kernel tail: fold partials, [all-reduce over NVLink peer memory], clip, Adam =================
-    // Only the 512 compute threads are left (the issuer warp has returned): named barrier 13, count 512.
+    // Only the 512 compute threads take part: named barrier 13, count 512.
     constexpr uint32_t BAR_TAIL = 13;
     const TailArgs& tl = g.tail;
     const AdamArgs& ad = tl.a;
     const int PP = ad.P;
-    float neg_step_size = ad.neg_step_size, bc2_sqrt = ad.bc2_sqrt;
-    uint32_t seq = tl.seq;
+    float neg_step_size = tl.neg_step_size_s[s], bc2_sqrt = tl.bc2_sqrt_s[s];
+    uint32_t seq = tl.seq + s;
     if (tl.ctrl != nullptr) {        // counters of a graph-replayed update live in device memory
-        neg_step_size = tl.ctrl->neg_step_size[tl.ordinal];
-        bc2_sqrt = tl.ctrl->bc2_sqrt[tl.ordinal];
-        seq = tl.ctrl->comm_seq + (uint32_t)tl.ordinal + 1u;
+        neg_step_size = tl.ctrl->neg_step_size[tl.ordinal + s];
+        bc2_sqrt = tl.ctrl->bc2_sqrt[tl.ordinal + s];
+        seq = tl.ctrl->comm_seq + (uint32_t)(tl.ordinal + s) + 1u;
     }
+    float* const loss_terms_out = tl.loss_terms_out != nullptr ? tl.loss_terms_out + LOSS_TERMS * s : nullptr;
+    const uint32_t bar_target = (s + 1u) * gridDim.x;      // the grid-barrier counters count on through the minibatches of the launch
     const int nparts = gridDim.x;
     float* tred = reinterpret_cast<float*>(sm + S::OFF_H1);              // [8][64] fold scratch (tiles are dead now)
     double* dred = reinterpret_cast<double*>(sm + S::OFF_H1 + 4096);     // [16] warp partials of the squared norm
@@ -621,7 +637,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         named_bar_sync(BAR_TAIL, TC_COMPUTE);
         if (tid == 0) {
             atomicAdd(ctr, 1u);
-            while (*reinterpret_cast<volatile uint32_t*>(ctr) < gridDim.x) { }
+            while (*reinterpret_cast<volatile uint32_t*>(ctr) < bar_target) { }
             __threadfence();
         }
         named_bar_sync(BAR_TAIL, TC_COMPUTE);
@@ -738,7 +754,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
             sbc[0] = cf < 1.0f ? cf : 1.0f;
             if (blockIdx.x == 0 && ad.norm_out) *ad.norm_out = norm;
         }
-    } else if (blockIdx.x == 0 && warp >= 1 && warp <= 5 && tl.loss_terms_out != nullptr) {
+    } else if (blockIdx.x == 0 && warp >= 1 && warp <= 5 && loss_terms_out != nullptr) {
         float t = 0.f;                                    // warp w folds loss term w-1 over the CTAs
         for (int c = lane; c < nparts; c += 32) t += __ldcg(g.loss_part + c * LOSS_TERMS + (warp - 1));
         t = warp_sum(t);
@@ -762,18 +778,36 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         if (ad.packed != nullptr) packed_store<O, A>(ad.packed, p, wgt);
     }
     TC_KSTAMP(10);
-    if (blockIdx.x == 0 && tid == 0 && tl.loss_terms_out != nullptr) {
+    if (blockIdx.x == 0 && tid == 0 && loss_terms_out != nullptr) {
         const float inv = 1.0f / (float)g.mb_count;
         const float pg = sbc[4] * inv, vl = 0.5f * sbc[5] * inv, en = sbc[6] * inv;
-        tl.loss_terms_out[0] = pg - g.ent_coef * en + vl * g.vf_coef;
-        tl.loss_terms_out[1] = pg; tl.loss_terms_out[2] = vl; tl.loss_terms_out[3] = en;
-        tl.loss_terms_out[4] = sbc[7] * inv; tl.loss_terms_out[5] = sbc[8] * inv;
-        tl.loss_terms_out[6] = 0.0f; tl.loss_terms_out[7] = 0.0f;
+        loss_terms_out[0] = pg - g.ent_coef * en + vl * g.vf_coef;
+        loss_terms_out[1] = pg; loss_terms_out[2] = vl; loss_terms_out[3] = en;
+        loss_terms_out[4] = sbc[7] * inv; loss_terms_out[5] = sbc[8] * inv;
+        loss_terms_out[6] = 0.0f; loss_terms_out[7] = 0.0f;
     }
-    if (tid == 0) {
+    if (s + 1 < nsteps) {
+        // next minibatch of the launch: every CTA has applied its slice of the Adam step (and refreshed its part of the packed
+        // weights) -> reload the weight tiles; the loader has the first [obs|1] tiles in the ring already
+        grid_barrier(tl.ctr + 1);
+        if (tid == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");      // other CTAs' generic-proxy stores -> this thread's TMA reads
+            mbar_expect_tx(bars, (uint32_t)S::W_BYTES);
+            const char* src = reinterpret_cast<const char*>(g.packed + P::TC_W2);
+            for (uint32_t off = 0; off < (uint32_t)S::W_BYTES; off += 16384u) {
+                const uint32_t nb = (uint32_t)S::W_BYTES - off < 16384u ? (uint32_t)S::W_BYTES - off : 16384u;
+                bulk_g2s(sm + S::OFF_W + off, src + off, nb, bars);
+            }
+        }
+    } else if (tid == 0) {
         __threadfence();
         if (atomicAdd(tl.ctr + 3, 1u) == gridDim.x - 1) { tl.ctr[0] = 0u; tl.ctr[1] = 0u; tl.ctr[2] = 0u; tl.ctr[3] = 0u; }   // re-arm
     }
+    }   // tail
+    }   // minibatches of the launch
+    umma::fence_before_sync();
+    __syncthreads();           // end of the kernel: with the issuer and the loader warp
+    if (warp == 1) umma::tmem_dealloc(tmem, TC_COLS);
 }
 
 template <int O, int A, int OP, int RW>

@@ -66,6 +66,9 @@ class PPOConfig:
     update_precision: str = "auto"   # "bf16": tcgen05 tensor-core update (bf16 operands, fp32 accumulate); "fp32": CUDA-core
                                      # update; "auto": bf16 from 2048 envs per rank (minibatches of >= 64k samples), else fp32
     debug_logits: bool = False       # record the logits every action was sampled from ([T][N][A] plane, parity tests)
+    steps_per_launch: int = 0        # tcgen05 fused step: minibatches per kernel launch (0 = auto: a whole epoch when its minibatches
+                                     # are equally sized, at most 8 and of at most 2^19 samples -- where the per-launch fixed costs
+                                     # matter -- else 1)
     cuda_graph: bool = True          # tcgen05 path: capture the launches of one update in a CUDA graph (counters live in a
                                      # device-resident drl_ctrl_t) and replay it; results are bit-identical to the eager path
 
@@ -207,6 +210,14 @@ class PPOTrainer:
         if (self.world > 1 and cfg.grad_allreduce == "peer" and self.grad_flags == 1 and cfg.hidden == 64
                 and torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.peer = _dist.PeerComm(self.net, self.rank, self.world, dev)
+        # minibatches per launch of the fused tensor-core step (a whole epoch when possible)
+        equal = B % cfg.minibatch_size == 0
+        self.mb_per_launch = 1
+        if self.grad_flags == 1 and cfg.hidden == 64 and equal and (self.world == 1 or self.peer is not None):
+            want = cfg.steps_per_launch if cfg.steps_per_launch > 0 else (self.n_mb if cfg.minibatch_size <= (1 << 19) else 1)
+            self.mb_per_launch = max(1, min(want, self.n_mb, 8))
+            while self.n_mb % self.mb_per_launch:
+                self.mb_per_launch -= 1
         self.timing = False        # record CUDA events around each phase (bench.py)
         self.phase_events: Dict[str, list] = {}
         # graph-replayable update: device-resident counters + one captured graph (tcgen05 fused step only)
@@ -333,14 +344,16 @@ class PPOTrainer:
                 torch.cuda.current_stream().wait_event(self._ev_stats[epoch])
             idx_ptr = self.idx[epoch].data_ptr()
             stats_ptr = self.adv_stats[epoch].data_ptr()
-            for k in range(self.n_mb):
+            for k in range(0, self.n_mb, self.mb_per_launch):
                 start = k * M
                 count = min(M, B - start)
                 row = epoch * self.n_mb + k
+                ns = self.mb_per_launch     # minibatches of this launch (equally sized when > 1)
                 if ctl:     # counters from the device control block: the launch is identical from update to update
-                    self.adam_step += 1
+                    self.adam_step += ns
                     if self.peer is not None:
-                        self.peer.next()
+                        for _ in range(ns):
+                            self.peer.next()
                     with _Phase(self, "minibatch_grad"):
                         _lib.check(self.L.drl_ppo_minibatch_update_ctl(
                             net, self.agent.packed.data_ptr(), self.records.data_ptr(), idx_ptr, start, count,
@@ -348,30 +361,37 @@ class PPOTrainer:
                             self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.ctrl.data_ptr(), row,
                             0.9, 0.999, 1e-5, cfg.max_grad_norm, self.loss_terms.data_ptr() + 32 * row,
                             self.grad_norm.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, self.grad_flags,
-                            C.byref(self.peer.struct) if self.peer is not None else None, st))
+                            C.byref(self.peer.struct) if self.peer is not None else None, ns, st))
                     self.kernel_launches += 1
                     continue
                 if self.peer is not None:
-                    self.adam_step += 1
+                    first_step = self.adam_step + 1
+                    self.adam_step += ns
+                    comm = self.peer.next()          # sequence number of the launch's first minibatch step
+                    for _ in range(ns - 1):
+                        self.peer.next()
+                    comm.seq = self.peer.seq - ns + 1
                     with _Phase(self, "minibatch_grad"):    # gradient + fold + NVLink all-reduce + clip + Adam: one launch
                         _lib.check(self.L.drl_ppo_minibatch_update_dist(
                             net, self.agent.packed.data_ptr(), self.records.data_ptr(), idx_ptr, start, count,
                             stats_ptr + 8 * k, C.byref(self.coef), self.agent.flat_params.data_ptr(),
-                            self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.adam_step, lr,
+                            self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), first_step, lr,
                             0.9, 0.999, 1e-5, cfg.max_grad_norm, self.loss_terms.data_ptr() + 32 * row,
                             self.grad_norm.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, self.grad_flags,
-                            C.byref(self.peer.next()), st))
+                            C.byref(comm), ns, st))
+                    comm.seq = self.peer.seq
                     self.kernel_launches += 1
                     continue
                 if self.world == 1 and self.fused_step:
-                    self.adam_step += 1
+                    first_step = self.adam_step + 1
+                    self.adam_step += ns
                     with _Phase(self, "minibatch_grad"):    # gradient kernel + fused fold/clip/Adam kernel
                         _lib.check(self.L.drl_ppo_minibatch_update(
                             net, self.agent.packed.data_ptr(), self.records.data_ptr(), idx_ptr, start, count,
                             stats_ptr + 8 * k, C.byref(self.coef), self.agent.flat_params.data_ptr(),
-                            self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.adam_step, lr,
+                            self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), first_step, lr,
                             0.9, 0.999, 1e-5, cfg.max_grad_norm, self.loss_terms.data_ptr() + 32 * row,
-                            self.grad_norm.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, self.grad_flags, st))
+                            self.grad_norm.data_ptr(), self.workspace.data_ptr(), self.ws_bytes, self.grad_flags, ns, st))
                     self.kernel_launches += 1 if self.grad_flags == 1 else 2
                     continue
                 with _Phase(self, "minibatch_grad"):

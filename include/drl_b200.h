@@ -206,13 +206,17 @@ int drl_comm_close(void* peer_ptr);
 int drl_comm_free(void* dev_ptr);
 
 /* ---- single-GPU fusion of the three calls above/below: minibatch gradient, then ONE cooperative kernel that folds
- * the per-CTA partial gradients, clips by the global norm and applies Adam (ppo.py:159-192 in two launches).
- * `packed` is read by the gradient kernels and refreshed by the Adam step; grad_out receives the pre-clip gradient. */
+ * the per-CTA partial gradients, clips by the global norm and applies Adam (ppo.py:159-192 in two launches; ONE launch on the
+ * tensor-core path).  `packed` is read by the gradient kernels and refreshed by the Adam step; grad_out receives the pre-clip gradient.
+ * num_steps (1..8; > 1 on the tensor-core path only): the launch runs that many CONSECUTIVE, equally sized minibatches -- minibatch s
+ * covers idx[mb_start + s * mb_count, +mb_count), normalises with adv_stats[2s], [2s+1], writes loss_terms_out[8s..8s+8) and applies
+ * optimizer step `step + s` -- i.e. a whole epoch of ppo.py:156-192 without leaving the kernel (the weight tiles are reloaded and the
+ * record gather of the next minibatch runs ahead while the fold / clip / Adam tail of the current one finishes). */
 int drl_ppo_minibatch_update(const drl_net_t* net, float* packed, const float* rec, const uint32_t* idx, uint32_t mb_start,
                              uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params, float* grad_out,
                              float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1, double beta2, double eps,
                              double max_grad_norm, float* loss_terms_out, float* norm_out, void* workspace, size_t workspace_bytes,
-                             uint32_t flags, void* stream);
+                             uint32_t flags, int32_t num_steps, void* stream);
 /* Multi-GPU form (tensor-core path only): the same single cooperative launch; between the local fold and the clip the
  * CTAs publish their gradient slices in the symmetric buffer, wait for every peer's arrival flag and sum the peers'
  * slices over NVLink in rank order (a one-shot all-reduce inside the kernel, identical result on every rank), then
@@ -221,7 +225,8 @@ int drl_ppo_minibatch_update_dist(const drl_net_t* net, float* packed, const flo
                                   uint32_t mb_count, const float* adv_stats, const drl_ppo_coef_t* coef, float* params,
                                   float* grad_out, float* exp_avg, float* exp_avg_sq, int64_t step, double lr, double beta1,
                                   double beta2, double eps, double max_grad_norm, float* loss_terms_out, float* norm_out,
-                                  void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm, void* stream);
+                                  void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm, int32_t num_steps,
+                                  void* stream);
 
 /* Graph-replayable form of the two calls above (tensor-core path): `ordinal` = index of this optimizer step inside the update
  * (Adam scalars ctrl->neg_step_size[ordinal], ctrl->bc2_sqrt[ordinal]; sequence number ctrl->comm_seq + ordinal + 1);
@@ -231,7 +236,7 @@ int drl_ppo_minibatch_update_ctl(const drl_net_t* net, float* packed, const floa
                                  float* grad_out, float* exp_avg, float* exp_avg_sq, const drl_ctrl_t* ctrl, int32_t ordinal,
                                  double beta1, double beta2, double eps, double max_grad_norm, float* loss_terms_out,
                                  float* norm_out, void* workspace, size_t workspace_bytes, uint32_t flags, const drl_comm_t* comm,
-                                 void* stream);
+                                 int32_t num_steps, void* stream);
 
 /* ---- clip_grad_norm_ + Adam, ppo.py:191-192 (after the gradient all-reduce) ----
  * grad is multiplied by grad_scale (1/world) first; `step` is the 1-based Adam step of this call.

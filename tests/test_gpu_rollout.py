@@ -519,3 +519,23 @@ def test_h256_trainer_learns_and_keeps_ratio_one():
     assert rets[0] < 40 and max(rets[-5:]) > 100, rets
     with pytest.raises(ValueError, match="tensor-core"):
         drl.PPOTrainer(drl.PPOConfig(num_envs=8, hidden=256, update_precision="fp32"))
+
+
+@pytest.mark.parametrize("env_id,N,T", [("CartPole-v1", 256, 32), ("Acrobot-v1", 64, 24)])
+def test_epoch_per_launch_is_bit_identical_to_one_minibatch_per_launch(env_id, N, T):
+    """drl_ppo_minibatch_update*(num_steps = 4): a whole epoch of ppo.py:156-192 inside one cooperative launch (weights reloaded and
+    the record gather running ahead between the minibatches) must equal four single-minibatch launches bit for bit."""
+    import deep_rl_b200 as drl
+    out = []
+    for spl in (1, 2, 4):
+        cfg = drl.PPOConfig(env_id=env_id, num_envs=N, num_steps=T, seed=9, total_timesteps=N * T * 8, update_precision="bf16",
+                            steps_per_launch=spl, cuda_graph=(spl == 4))
+        tr = drl.PPOTrainer(cfg)
+        assert tr.mb_per_launch == spl
+        for _ in range(5):
+            tr.update(8)
+        torch.cuda.synchronize()
+        out.append((tr.agent.flat_params.clone(), tr.exp_avg_sq.clone(), tr.loss_terms.clone(), tr.grad.clone(), tr.grad_norm.clone()))
+    for o in out[1:]:
+        for a, b in zip(out[0], o):
+            assert torch.equal(a, b)
