@@ -529,12 +529,12 @@ def run_b200(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"{'ppo_grad_tc_kernel' if tc else 'ppo_grad_kernel'}@{M}")
+            tj = json.load(open(tpath))
+            kname = 'ppo_grad_tc_kernel' if tc else 'ppo_grad_kernel'
+            traffic = tj.get(f"{kname}@{M}x{tr.mb_per_launch}") if tr.mb_per_launch > 1 else tj.get(f"{kname}@{M}")
         except Exception:
             traffic = None
     mb_per_launch = tr.mb_per_launch
-    if traffic is not None:
-        traffic = traffic * mb_per_launch
     roofline = _grad_roofline(args.env_id, hidden, M * mb_per_launch, phases, local_ms, value, world, tc, peaks, traffic)
     roofline.update({
         "minibatches_per_launch": mb_per_launch,
