@@ -38,18 +38,64 @@ __global__ void __launch_bounds__(256) env_observe_kernel(drl_env_t env, float* 
     for (int q = 0; q < OP / 4; ++q) o4[q] = make_float4(obs[4 * q], obs[4 * q + 1], obs[4 * q + 2], obs[4 * q + 3]);
 }
 
+// The finished-episode log is aggregated per BLOCK here (one atomicAdd on the counter and one per sum for up to 256 envs): with
+// millions of envs and an untrained policy ~5 % of them finish in every step, and even warp-aggregated atomics on three
+// addresses (drl_env.cuh) would then bound the kernel instead of HBM.
 template <int KIND>
 __global__ void __launch_bounds__(256) env_step_kernel(drl_env_t env, uint64_t step, const int32_t* __restrict__ actions,
                                                         float* __restrict__ obs_out, float* __restrict__ rew_out,
                                                         uint8_t* __restrict__ done_out, drl_ep_log_t log) {
     constexpr int OP = EnvSpec<KIND>::OP;
+    __shared__ uint32_t w_cnt[8], w_base[8];
+    __shared__ double w_ret[8], w_len[8];
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= env.num_envs) return;
+    const bool live = n < env.num_envs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t gid = env.env_gid0 + (uint32_t)n;
     EnvLane e;
-    env_load(e, env, n);
-    float reward;
-    const bool done = env_step<KIND>(e, actions[n], reward, env.seed, env.env_gid0 + (uint32_t)n, step,
-                                     env.max_episode_steps, log);
+    e.s[0] = e.s[1] = e.s[2] = e.s[3] = 0.0; e.elapsed = 0; e.ep_ret = 0.0f; e.ep_len = 0;
+    float reward = 0.0f;
+    bool done = false;
+    if (live) {
+        env_load(e, env, n);
+        const bool term = env_physics<KIND>(e.s, actions[n], reward);
+        e.elapsed += 1;                                   // TimeLimit + RecordEpisodeStatistics, as env_after_physics
+        done = term || (e.elapsed >= env.max_episode_steps);
+        e.ep_ret = e.ep_ret + reward;
+        e.ep_len += 1;
+    }
+    if (log.count != nullptr) {
+        const unsigned dmask = __ballot_sync(0xffffffffu, done);
+        double sr = done ? (double)e.ep_ret : 0.0, sl = done ? (double)e.ep_len : 0.0;
+        sr = warp_sum(sr); sl = warp_sum(sl);
+        if (lane == 0) { w_cnt[warp] = (uint32_t)__popc(dmask); w_ret[warp] = sr; w_len[warp] = sl; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            double tr = 0.0, tl = 0.0;
+            for (int w = 0; w < 8; ++w) { w_base[w] = tot; tot += w_cnt[w]; tr += w_ret[w]; tl += w_len[w]; }
+            if (tot > 0) {
+                const uint32_t base = atomicAdd(log.count, tot);
+                if (log.sum_ret) atomicAdd(log.sum_ret, tr);
+                if (log.sum_len) atomicAdd(log.sum_len, tl);
+                for (int w = 0; w < 8; ++w) w_base[w] += base;
+            }
+        }
+        __syncthreads();
+        if (done) {
+            const uint32_t slot = w_base[warp] + (uint32_t)__popc(dmask & ((1u << lane) - 1u));
+            if (slot < log.cap && log.entries) {
+                drl_ep_entry_t en;
+                en.step = step; en.env = gid; en.ret = e.ep_ret; en.len = e.ep_len; en.pad = 0u;
+                log.entries[slot] = en;
+            }
+        }
+    }
+    if (!live) return;
+    if (done) {
+        env_reset_state<KIND>(e.s, env.seed, gid, step);
+        e.elapsed = 0; e.ep_ret = 0.0f; e.ep_len = 0;
+    }
     env_store(e, env, n);
     float obs[OP];
     env_observation<KIND>(e.s, obs);

@@ -74,18 +74,30 @@ __global__ void __launch_bounds__(256) priority_block_sums_kernel(const float* _
     if (lane == 0) { bsum[warp] = s; bsum_alpha[warp] = sa; }
 }
 
-// pass 2 (one thread): exclusive prefix of the block sums, sequentially; totals at [nblk]
-__global__ void priority_block_prefix_kernel(double* __restrict__ bsum, double* __restrict__ bsum_alpha, uint32_t nblk) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// pass 2 (one warp): exclusive prefix of the block sums in sequential (left to right) order; totals at [nblk].  The warp stages
+// 2048 sums at a time in shared memory with coalesced loads, lane 0 adds them up in order -- the association of a plain loop,
+// without 4096 dependent global-memory round trips.
+__global__ void __launch_bounds__(32) priority_block_prefix_kernel(double* __restrict__ bsum, double* __restrict__ bsum_alpha, uint32_t nblk) {
+    __shared__ double sh[2048], sha[2048];
+    const int lane = threadIdx.x;
     double run = 0.0, runa = 0.0;
-    for (uint32_t b = 0; b < nblk; ++b) {
-        const double s = bsum[b];
-        bsum[b] = run;
-        run += s;
-        runa += bsum_alpha[b];
+    for (uint32_t b0 = 0; b0 < nblk; b0 += 2048) {
+        const uint32_t nb = min(2048u, nblk - b0);
+        for (uint32_t i = lane; i < nb; i += 32) { sh[i] = bsum[b0 + i]; sha[i] = bsum_alpha[b0 + i]; }
+        __syncwarp();
+        if (lane == 0) {
+            for (uint32_t i = 0; i < nb; ++i) {
+                const double s = sh[i];
+                sh[i] = run;
+                run += s;
+                runa += sha[i];
+            }
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < nb; i += 32) bsum[b0 + i] = sh[i];
+        __syncwarp();
     }
-    bsum[nblk] = run;
-    bsum_alpha[nblk] = runa;
+    if (lane == 0) { bsum[nblk] = run; bsum_alpha[nblk] = runa; }
 }
 
 // pass 3: draw i: target = u * total (u = (w + 0.5) / 2^32 in float64); the last block whose exclusive prefix is <= target, then a
