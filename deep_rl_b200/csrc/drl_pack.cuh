@@ -87,8 +87,8 @@ inline WorkspaceLayout workspace_layout(int64_t P, int hidden = 64) {
                                                            // every region up to here has a size independent of P
     w.loss_partials = w.ev_partials + sizeof(double) * STAT_PARTS * 4;
     w.grad_partials = w.loss_partials + sizeof(float) * MAX_GRAD_CTAS * LOSS_TERMS;
-    w.debug = w.grad_partials + sizeof(float) * (size_t)MAX_GRAD_CTAS * w.ppad;   // 4 KB of cycle stamps (DRL_TC_DEBUG=1)
-    w.stage = (w.debug + 4096 + 1023) / 1024 * 1024;
+    w.debug = (w.grad_partials + sizeof(float) * (size_t)MAX_GRAD_CTAS * w.ppad + 1023) / 1024 * 1024;   // 4 KB of cycle stamps
+    w.stage = w.debug + 4096;                       // (-DDRL_TC_STAMPS builds; hidden = 64: the LAST 4 KB of the workspace)
     w.total = w.stage + (hidden == 256 ? (size_t)2 * 2 * 4096 * 65536 : 0);
     return w;
 }

@@ -55,11 +55,15 @@ struct TcSmem {
     static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
-// diagnostics: cycle stamps of CTA 0 (slot = tile * 16 + event), enabled with DRL_TC_DEBUG=1
+// diagnostics, only in a -DDRL_TC_STAMPS build (profiles/tc_stamps.py): cycle stamps of CTA 0 (slot = tile * 16 + event) and
+// whole-kernel stamps of CTA 0 / thread 0 (slots 8..15 of the issuer rows of the debug block)
+#ifdef DRL_TC_STAMPS
 #define TC_STAMP(ev) do { if (g.dbg != nullptr && blockIdx.x == 0 && lane == 0 && k < 12 && (warp == 0 || warp == TC_COMPUTE / 32)) g.dbg[(warp == 0 ? 0 : 256) + k * 16 + (ev)] = clock64(); } while (0)
-
-// whole-kernel stamps of CTA 0 (thread 0): slots 8..15 of the issuer rows of the debug block
 #define TC_KSTAMP(n) do { if (g.dbg != nullptr && blockIdx.x == 0 && tid == 0) g.dbg[256 + ((n) >> 3) * 16 + 8 + ((n) & 7)] = clock64(); } while (0)
+#else
+#define TC_STAMP(ev) do { } while (0)
+#define TC_KSTAMP(n) do { } while (0)
+#endif
 
 enum : uint32_t { BAR_FWD = 1, BAR_BWD = 2, BAR_W1 = 3, BAR_PAIR0 = 4, BAR_L1 = 12 };   // named barriers (0 = __syncthreads)
 
@@ -263,7 +267,9 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
                         umma::mma(tmem + C_DH + n2 * 64, umma::make_desc(aDZ + n2 * 16384 + kb * 32, 16, 1024, umma::LAYOUT_SW128),
                                   umma::make_desc(aW2 + n2 * 8192 + kb * 2048, 8192, 1024, umma::LAYOUT_SW128), ID_DH1, kb > 0);
                 umma::commit(bars + 2);          // dh1 is all that Z(k) waits for
+#ifdef DRL_TC_STAMPS
                 if (g.dbg != nullptr && blockIdx.x == 0 && k < 12) g.dbg[256 + k * 16 + 6] = clock64();
+#endif
             }
             __syncwarp();
             TC_STAMP(1);

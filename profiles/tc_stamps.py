@@ -1,4 +1,5 @@
-"""Cycle-stamp timeline of ppo_grad_tc_kernel (CTA 0), DRL_TC_DEBUG=1.  Usage: DRL_TC_DEBUG=1 python profiles/tc_stamps.py"""
+"""Cycle-stamp timeline of ppo_grad_tc_kernel (CTA 0).  Needs a library built with -DDRL_TC_STAMPS:
+   DRL_EXTRA_NVCC_FLAGS=-DDRL_TC_STAMPS python -c "import __graft_entry__ as g; g.build()"; python profiles/tc_stamps.py 4096"""
 import os
 import sys
 

@@ -37,10 +37,10 @@ def main():
         L.check(lib.drl_ppo_minibatch_grad(C.byref(net), packed.data_ptr(), rec.data_ptr(), idx.data_ptr(), 0, M, stats.data_ptr(),
                                            C.byref(cf), grad.data_ptr(), terms.data_ptr(), ws.data_ptr(), nb, 1, L.stream_ptr()))
     torch.cuda.synchronize()
-    # debug block = 4 KB before the (1024-aligned) staging region
+    # debug block = 4 KB (1024-aligned) right before the staging region
     raw = ws.cpu().numpy()
     P4 = (P + 3) // 4 * 4
-    off_debug = 64 + 8 * 16 * 512 * 2 + 8 * 1024 + 8 * 512 * 4 + 4 * 160 * 8 + 4 * 160 * P4
+    off_debug = (64 + 8 * 16 * 512 * 2 + 8 * 1024 + 8 * 512 * 4 + 4 * 160 * 8 + 4 * 160 * P4 + 1023) // 1024 * 1024
     st = raw[off_debug:off_debug + 4096].view(np.int64)
     for k in range(2, 6):
         row = st[k * 16:k * 16 + 14]
