@@ -14,7 +14,8 @@ KEEP = re.compile(
     r"sm__warps_active.avg.pct|launch__(registers_per_thread|grid_size|block_size|occupancy_limit|shared_mem_per_block_dynamic)|"
     r"sm__inst_executed_pipe_(fma|lsu|xu|alu|fp64|tensor).*pct_of_peak_sustained_active$|sm__pipe_(fma|tensor|fp64|alu).*cycles_active.avg.pct_of_peak_sustained_active$|"
     r"smsp__issue_active.avg.pct|smsp__inst_executed.sum$|l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum$|"
-    r"l1tex__data_pipe_lsu_wavefronts_mem_shared.sum$|sm__cycles_elapsed.avg$|smsp__average_warps_issue_stalled_.*_per_issue_active.ratio$|"
+    r"l1tex__data_pipe_(lsu|tc)_wavefronts_mem_shared(_op_ld|_op_st)?.sum(.pct_of_peak_sustained_elapsed)?$|sm__cycles_elapsed.avg$|"
+    r"l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_(ld|st).sum$|smsp__average_warps_issue_stalled_.*_per_issue_active.ratio$|"
     r"lts__t_sector_hit_rate.pct|l1tex__t_sector_hit_rate.pct|smsp__cycles_active.avg$|sm__cycles_active.avg$")
 
 
