@@ -258,6 +258,7 @@ def _timed_updates(tr, nu, steps, flush, dist, dev, instrument=False):
     torch.cuda.synchronize()
     for _ in range(steps):
         flush.zero_()
+        tr.env.log.clear()      # as a caller that reads the episode records after every update leaves it (the e2e leg does read them)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         tr.update(nu)
@@ -540,9 +541,11 @@ def run_b200(args):
         "minibatches_per_launch": mb_per_launch,
         "kernel_launch_includes": (f"{mb_per_launch} consecutive minibatch steps (one epoch), each = gradient + fold of the per-SM partials + clip + Adam, "
                                    "in ONE cooperative launch") if tc else "gradient kernel only",
-        "limiter": ("no single pipe: per 128-sample tile a MUFU-bound tanh section, an issue-bound FMA section and three ~600-cycle "
-                    "tcgen05 round trips run back to back (one tile in flight per SM); the small GEMM instructions are bound by "
-                    "operand fetch from shared memory, not math (DESIGN.md section 3, profiles/tools/mma_timing.cu)" if tc else "FP32 FMA issue"),
+        "limiter": ("the shared-memory data pipe: operand fetch of the small-N tcgen05 GEMMs (35 % of its peak at C3) + the compute warps' "
+                    "bf16 tile stores and broadcast weight loads (53 %), ncu l1tex__data_pipe_{tc,lsu}_wavefronts_mem_shared in "
+                    "profiles/r2_grad_tc_c3_full.txt; then issue slots (57 %) and the XU pipe (tanh + bf16 packs, 35 %); at this "
+                    "minibatch size a third of the launch is the per-minibatch tail (fold, three grid barriers, clip, Adam, weight reload) "
+                    "-- DESIGN.md section 3" if tc else "FP32 FMA issue"),
         "note": ("tcgen05 path: every GEMM of the two MLPs (layers 1-2 forward, dh1, all weight-gradient reductions) runs on the "
                  "tensor pipe (bf16 operands, fp32 TMEM accumulators); FLOPs counted are the algorithmic 3F per sample; launch_ms is the "
                  "whole minibatch-step call (the gradient kernel carries the fold + clip + Adam tail)" if tc else
