@@ -168,6 +168,32 @@ __device__ __forceinline__ int sample_categorical(const float (&l)[A], float u, 
     return act;
 }
 
+// The same draw with the log-probability left in two pieces, logp = diff - logf(sum): the fused rollout finishes it off the
+// critical path of the step.  Bit-identical to sample_categorical.
+template <int A>
+__device__ __forceinline__ int sample_categorical_split(const float (&l)[A], float u, float& diff, float& sum) {
+    float m = l[0];
+#pragma unroll
+    for (int a = 1; a < A; ++a) m = l[a] > m ? l[a] : m;
+    float e[A];
+    float s = 0.0f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) { e[a] = exp_det(__fsub_rn(l[a], m)); s = __fadd_rn(s, e[a]); }
+    float thr = __fmul_rn(u, s);
+    float c = 0.0f;
+    int act = A - 1;
+    bool found = false;
+    float lsel = l[A - 1];
+#pragma unroll
+    for (int a = 0; a < A - 1; ++a) {
+        c = __fadd_rn(c, e[a]);
+        if (!found && thr < c) { act = a; lsel = l[a]; found = true; }
+    }
+    diff = __fsub_rn(lsel, m);
+    sum = s;
+    return act;
+}
+
 // tanh with two MUFU ops (ex2, rcp): |abs err| ~ 2e-7; saturates correctly at +-1.
 __device__ __forceinline__ float tanh_fast(float x) {
     float t, r;

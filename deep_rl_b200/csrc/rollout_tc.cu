@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(drl_env_t env
     EnvLane e;
     e.s[0] = e.s[1] = e.s[2] = e.s[3] = 0.0; e.elapsed = 0; e.ep_ret = 0.0f; e.ep_len = 0;
     if (own) env_load(e, env, n);
+    float lp_diff = 0.0f, lp_sum = 1.0f;     // (l_act - max) and the softmax denominator of the previous step's draw
 
     for (int t = 0; t <= T; ++t) {
         // ---- S0: observation of the current state ----
@@ -265,6 +266,17 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(drl_env_t env
         named_bar_arrive(RB_FWD, TC_THREADS);
         RO_STAMP(4);
 
+        // ---- owners, while the GEMM runs: the pieces of S3 that do not depend on this step's logits.  The owner threads are the
+        // critical path of a step (S3 -> S0 -> group barrier); here they would only spin on the mbarrier. ----
+        uint4 rr = make_uint4(0u, 0u, 0u, 0u);
+        if (own) {
+            if (t > 0) buf.logp[(size_t)(t - 1) * N + n] = __fsub_rn(lp_diff, logf(lp_sum));   // log-prob of step t-1: (l_act - max) - log(sum)
+            if (t < T) {
+                const uint64_t step = step0 + (uint64_t)t;
+                rr = philox_seeded(env.seed, gid, (uint32_t)step, (uint32_t)(step >> 32), TAG_ACTION);
+            }
+        }
+
         // ---- S2: layer-2 epilogue and partial head dot products ----
         mbar_wait(bars + 1, (uint32_t)t & 1u);
         umma::fence_after_sync();
@@ -328,13 +340,10 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(drl_env_t env
                 }
                 RO_STAMP(8);
                 const uint64_t step = step0 + (uint64_t)t;
-                const uint4 rr = philox_seeded(env.seed, gid, (uint32_t)step, (uint32_t)(step >> 32), TAG_ACTION);
                 RO_STAMP(9);
-                float lp;
-                const int act = sample_categorical<A>(l, u01_f32(rr.x), lp);
+                const int act = sample_categorical_split<A>(l, u01_f32(rr.x), lp_diff, lp_sum);   // log-prob finished during the next GEMM wait
                 RO_STAMP(10);
                 buf.act[i0] = (uint8_t)act;
-                buf.logp[i0] = lp;
                 float reward;
                 bool term;
                 if (SPECULATE) {          // the env warp has evaluated every action: take the sampled one
