@@ -12,7 +12,9 @@
 // The threads with half = net = replica = 0 additionally own the env state (float64 registers).  Per step:
 //   S0  owners: observation from state -> obs[t] in HBM and the fp32 obs tile in shared memory
 //   --  group barrier (the 4*REP warps that share 32 environments)
-//   S1  all: layer 1 on CUDA cores for 32/REP units -> bf16 SW128 tile (all REP rows of the env); hand the forward GEMM
+//   S1  all: layer 1 on CUDA cores for 32/REP units -> bf16 SW128 tile (all REP rows of the env); hand the forward GEMM.
+//       REP = 1 (throughput regime): layer 1 is a K = 16 GEMM as in update_tc.cu -- the owners write the bf16 [obs_hi|1|obs_lo]
+//       row in S0, the issuer runs z1 = [obs_hi|1|obs_lo] . [W1|b1|W1]^T, S1 is tcgen05.ld + tanh + tile store
 //   S2  all: wait, tcgen05.ld z2, tanh, partial head dot products -> exchange buffer
 //   --  group barrier
 //   ENV  four extra warps (one per 32 env rows, lane = env): the fp64 physics of the step for EVERY action, from the state the
@@ -36,7 +38,8 @@ __device__ long long g_ro_dbg[1024];
 #else
 #define RO_STAMP(ev) do { } while (0)
 #endif
-enum : uint32_t { RB_FWD = 1, RB_ROW0 = 2, RB_ROW1 = 6 };   // named barriers: issuer hand-off; per row group: state published (2..5), step evaluated (6..9)
+enum : uint32_t { RB_FWD = 1, RB_ROW0 = 2, RB_ROW1 = 6, RB_L1 = 10 };   // named barriers: issuer hand-off; per row group: state published (2..5), step evaluated (6..9);
+                                                                        // REP = 1: the owners' [obs|1] rows are written (owners arrive, issuer syncs)
 
 template <int O, int A>
 struct RoTcSmem {
@@ -45,7 +48,8 @@ struct RoTcSmem {
     static constexpr int OFF_W = 0;
     static constexpr int OFF_H1 = (OFF_W + W_BYTES + 1023) / 1024 * 1024;   // (actor, critic) x 16 KB
     static constexpr int OFF_OBS = OFF_H1 + 32768;                           // fp32 [128][OW]
-    static constexpr int OFF_XCH = OFF_OBS + TC_TILE * P::OW * 4;            // fp32 [32 slots][128] head partial sums
+    static constexpr int OBS_BYTES = TC_TILE * P::OW * 4 > 4096 ? TC_TILE * P::OW * 4 : 4096;   // REP = 1: the bf16 NS16 operand tile [128][16] instead
+    static constexpr int OFF_XCH = OFF_OBS + OBS_BYTES;                      // fp32 [32 slots][128] head partial sums
     static constexpr int OFF_ST = OFF_XCH + 32 * TC_TILE * 4;                // published env state: double [128][4]
     static constexpr int OFF_CAND = OFF_ST + TC_TILE * 32;                   // candidates: double [3 actions][128][4] + {reward, term} [3][128]
     static constexpr int OFF_BAR = OFF_CAND + 3 * TC_TILE * 32 + 3 * TC_TILE * 8;
@@ -87,8 +91,10 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(drl_env_t env
     double* st_s = reinterpret_cast<double*>(sm + S::OFF_ST);
     double* cand_s = reinterpret_cast<double*>(sm + S::OFF_CAND);
     float2* cand_rt = reinterpret_cast<float2*>(sm + S::OFF_CAND + 3 * TC_TILE * 32);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd
-    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);   // 0 weights, 1 fwd, 2 layer 1 (REP = 1)
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 3);
+    unsigned char* tW1B = reinterpret_cast<unsigned char*>(const_cast<float*>(sB4 + 4));   // bf16 layer-1 B tiles [W1|b1|W1] (drl_pack.cuh)
+    unsigned char* tOBS = sm + S::OFF_OBS;                           // REP = 1: NS16 [obs_hi|1|obs_lo] rows
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool is_mma_warp = warp == TC_COMPUTE / 32;
@@ -96,6 +102,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(drl_env_t env
     if (tid == 0) {
         mbar_init(bars, 1);
         mbar_init(bars + 1, 1);
+        mbar_init(bars + 2, 1);
         mbar_fence_init();
     }
     if (is_mma_warp) umma::tmem_alloc(slot, 128);
@@ -116,7 +123,21 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(drl_env_t env
     if (is_mma_warp) {
         const uint32_t aW2 = smem_u32(tW2), aH1 = smem_u32(tH1);
         constexpr uint32_t ID_FWD = umma::make_idesc(128, 64, false, false);
+        const uint32_t aW1B = smem_u32(tW1B), aOBS = smem_u32(tOBS);
+        constexpr uint32_t ID_L1 = umma::make_idesc(128, 64, false, false);
         for (int t = 0; t <= T; ++t) {
+            if (REP == 1) {       // layer 1: both operands K-major without swizzle, K = 16
+                named_bar_sync(RB_L1, 128 + 32);
+                umma::fence_after_sync();
+                if (umma::elect_one()) {
+#pragma unroll
+                    for (int n2 = 0; n2 < 2; ++n2)
+                        umma::mma(tmem + n2 * 64, umma::make_desc(aOBS, 2048, 128, umma::LAYOUT_NONE),
+                                  umma::make_desc(aW1B + n2 * 2048, 1024, 128, umma::LAYOUT_NONE), ID_L1, 0u);
+                    umma::commit(bars + 2);
+                }
+                __syncwarp();
+            }
             named_bar_sync(RB_FWD, TC_THREADS);
             umma::fence_after_sync();
             if (umma::elect_one()) {
@@ -203,22 +224,56 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(drl_env_t env
                 sp[0] = make_double2(e.s[0], e.s[1]);
                 sp[1] = make_double2(e.s[2], e.s[3]);
             }
-            // layer-1 input as the update's GEMM sees it: obs = hi + lo with both halves rounded to bf16 (update_tc.cu loader)
+            if (REP == 1) {
+                // the update's layer-1 operand row [obs_hi | 1 | obs_lo] (update_tc.cu loader): the issuer runs the same K = 16 GEMM
+                float o16[16];
 #pragma unroll
-            for (int i = 0; i < OP; ++i) {
-                const float hi = __bfloat162float(__float2bfloat16_rn(obs[i]));
-                obs[i] = hi + __bfloat162float(__float2bfloat16_rn(obs[i] - hi));
+                for (int i = 0; i < 16; ++i) o16[i] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < O; ++i) {
+                    const float hi = __bfloat162float(__float2bfloat16_rn(obs[i]));
+                    o16[i] = hi;
+                    o16[8 + i] = obs[i] - hi;
+                }
+                o16[O] = 1.0f;
+                umma::store_row_ns16(tOBS, TC_TILE, er, o16);
+                umma::fence_proxy_async();
+                umma::fence_before_sync();
+                named_bar_arrive(RB_L1, 128 + 32);
+            } else {
+                // layer-1 input as the update's GEMM sees it: obs = hi + lo with both halves rounded to bf16 (update_tc.cu loader)
+#pragma unroll
+                for (int i = 0; i < OP; ++i) {
+                    const float hi = __bfloat162float(__float2bfloat16_rn(obs[i]));
+                    obs[i] = hi + __bfloat162float(__float2bfloat16_rn(obs[i] - hi));
+                }
+#pragma unroll
+                for (int qq = 0; qq < OP / 4; ++qq)
+                    *reinterpret_cast<float4*>(obs_s + er * OW + 4 * qq) = make_float4(obs[4 * qq], obs[4 * qq + 1], obs[4 * qq + 2], obs[4 * qq + 3]);
             }
-#pragma unroll
-            for (int qq = 0; qq < OP / 4; ++qq)
-                *reinterpret_cast<float4*>(obs_s + er * OW + 4 * qq) = make_float4(obs[4 * qq], obs[4 * qq + 1], obs[4 * qq + 2], obs[4 * qq + 3]);
         }
         RO_STAMP(1);
         named_bar_sync(RB_ROW0 + grp, 128 * REP + 32);
         RO_STAMP(2);
 
         // ---- S1: layer 1 (UPT units of this thread's net) -> bf16 tile rows of every replica, hand the forward GEMM ----
-        {
+        if (REP == 1) {
+            mbar_wait(bars + 2, (uint32_t)t & 1u);
+            umma::fence_after_sync();
+            float h[UPT];
+            umma::ldn<UPT>(trow + net * 64 + u0, h);
+#pragma unroll
+            for (int j = 0; j < UPT; ++j) h[j] = tanh_mufu(h[j]);
+#pragma unroll
+            for (int c = 0; c < UPT / 8; ++c) {
+                uint4 ch;
+                ch.x = umma::pack_bf16(h[8 * c + 0], h[8 * c + 1]);
+                ch.y = umma::pack_bf16(h[8 * c + 2], h[8 * c + 3]);
+                ch.z = umma::pack_bf16(h[8 * c + 4], h[8 * c + 5]);
+                ch.w = umma::pack_bf16(h[8 * c + 6], h[8 * c + 7]);
+                *reinterpret_cast<uint4*>(tH1 + net * 16384 + umma::sw128_off(q * 32 + lane, u0 / 8 + c)) = ch;
+            }
+        } else {
             float x[OW];
 #pragma unroll
             for (int qq = 0; qq < OW / 4; ++qq) {
