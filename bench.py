@@ -322,7 +322,7 @@ def _env_step_roofline(env_id, dev, peaks, n_envs=1 << 22, steps=20):
     """One-off timing of the stand-alone env_step_kernel (drl_env_step: state in HBM) on n_envs environments."""
     import torch
     import deep_rl_b200 as drl
-    env = drl.make(env_id, num_envs=n_envs, seed=3, device=dev)
+    env = drl.make(env_id, num_envs=n_envs, seed=3, device=dev, log_capacity=1 << 22)   # ~200 k episodes end per step
     env.reset()
     act = torch.randint(0, env.num_actions, (n_envs,), dtype=torch.int32, device=dev)
     import ctypes as C

@@ -166,9 +166,9 @@ class VecEnv:
         self.ep_len = torch.zeros(N, dtype=torch.int32, device=self.device)
         if log_capacity is None:
             # enough for every episode that can finish between two drains of a 256-step rollout (an untrained CartPole policy
-            # lasts >= 8 steps), 24 B per entry, bounded at 4 Mi entries; beyond it entries are dropped and COUNTED
-            # (metrics()["episodes_dropped"])
-            log_capacity = min(max(1 << 16, N * 32), 1 << 22)
+            # lasts >= 8 steps), 24 B per entry, bounded at 16 Mi entries (403 MB: the 1 Mi-env stress config finishes ~12 M
+            # episodes per 256-step rollout); beyond it entries are dropped and COUNTED (metrics()["episodes_dropped"])
+            log_capacity = min(max(1 << 16, N * 32), 1 << 24)
         self.log = EpisodeLog(log_capacity, self.device)
         self.step_count = 0          # global step index fed to the Philox counter
         self._seed = int(seed)

@@ -6,7 +6,7 @@ import deep_rl_b200 as drl
 from deep_rl_b200 import _lib
 for env_id, nbytes in (("CartPole-v1", 94), ("Acrobot-v1", 102)):
     n = 1 << 22
-    env = drl.make(env_id, num_envs=n, seed=3)
+    env = drl.make(env_id, num_envs=n, seed=3, log_capacity=1 << 22)
     env.reset()
     act = torch.randint(0, env.num_actions, (n,), dtype=torch.int32, device=env.device)
     call = lambda k: _lib.check(env.L.drl_env_step(C.byref(env.struct), k, act.data_ptr(), env._obs.data_ptr(), env._rew.data_ptr(),
