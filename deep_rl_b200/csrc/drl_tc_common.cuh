@@ -17,10 +17,14 @@ __device__ __forceinline__ float tanh_mufu(float x) {
     return y;
 }
 
+// bar.sync / bar.arrive are warp-aligned instructions: every caller is a whole warp, and the __syncwarp() makes sure the warp has
+// reconverged after lane-divergent code (live / padding rows, env physics branches) before it executes them
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
+    __syncwarp();
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t count) {
+    __syncwarp();
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 // four 16-byte chunks (32 bf16) of row `row` of a SW128 tile, starting at chunk c0
