@@ -763,6 +763,7 @@ __global__ void __launch_bounds__(B_BLOCK, 1) dw2_gemm256_kernel(const unsigned 
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         mbar_wait(bars + 2 * B_STAGES, 0);
         umma::fence_after_sync();
+        named_bar_sync(1, 128);      // all four warps are done reading the stage ring (db2 sums) before any of them reuses it below
         // The accumulator row of a thread is one row of dW2 (1 KB): written straight from registers, a warp would touch 32
         // different lines per instruction.  Each 32 x 32 block goes through shared memory instead (the stage ring is idle now)
         // and leaves as 32 coalesced 128-byte rows.
