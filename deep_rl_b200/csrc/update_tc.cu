@@ -638,13 +638,17 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
     float* tred = reinterpret_cast<float*>(sm + S::OFF_H1);              // [8][64] fold scratch (tiles are dead now)
     double* dred = reinterpret_cast<double*>(sm + S::OFF_H1 + 4096);     // [16] warp partials of the squared norm
     float* sbc = reinterpret_cast<float*>(sm + S::OFF_H1 + 8192);        // broadcast slot
-    auto grid_barrier = [&](uint32_t* ctr) {      // all CTAs are co-resident (cooperative launch)
-        __threadfence();
+    // All CTAs are co-resident (cooperative launch).  The CTA's writes are ordered before thread 0's release-increment by the
+    // named barrier (the release is cumulative), the acquire-load orders the other CTAs' writes before everything after the
+    // second named barrier: one thread fences, once per side, instead of a sequentially-consistent fence in all 512.
+    auto grid_barrier = [&](uint32_t* ctr) {
         named_bar_sync(BAR_TAIL, TC_COMPUTE);
         if (tid == 0) {
-            atomicAdd(ctr, 1u);
-            while (*reinterpret_cast<volatile uint32_t*>(ctr) < bar_target) { }
-            __threadfence();
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+            uint32_t seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+            } while (seen < bar_target);
         }
         named_bar_sync(BAR_TAIL, TC_COMPUTE);
     };
