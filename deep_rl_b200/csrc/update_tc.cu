@@ -51,7 +51,8 @@ struct TcSmem {
     static constexpr int OFF_BAR = OFF_SCAL + 3 * 2048;   // 13 mbarriers + TMEM slot
     static constexpr int OFF_XCH = OFF_BAR + 128;      // head partial sums [net][half][A][128 rows] fp32
     static constexpr int OFF_RED = OFF_XCH + 2 * 2 * 4 * 128 * 4;
-    static constexpr int TOTAL = OFF_RED + 16 * 12 * 4 + 1024;   // + alignment slack
+    static constexpr int OFF_CTX = OFF_RED + 16 * 12 * 4;        // TailCtx: the tail's arguments, copied from the kernel parameters once
+    static constexpr int TOTAL = OFF_CTX + 512 + 1024;           // + alignment slack
     static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
@@ -78,8 +79,223 @@ __device__ __forceinline__ uint32_t tc_sample_index(const GradArgs& g, uint32_t 
     return g.idx ? __ldg(g.idx + i) : i;
 }
 
+// What the tail reads of the kernel parameters.  The tail is a separate function, and a reference to the parameter block would
+// turn every field access into a generic load; thread 0 copies the block into shared memory once per launch instead.
+struct TailCtx {
+    TailArgs tl;
+    float* grad_part; float* loss_part; float* packed; long long* dbg;
+    int ppad; uint32_t mb_count; float ent_coef, vf_coef;
+};
+static_assert(sizeof(TailCtx) <= 512, "TailCtx block");
+
+// ================= in-kernel tail of one minibatch: fold partials, [all-reduce over NVLink peer memory], clip, Adam, reload =================
+// Only the 512 compute threads take part: named barrier 13, count 512.  A separate (not inlined) function: its registers (20
+// loads in flight in the fold, the Adam state) are then allocated apart from the tile loop's, which otherwise spills.
+template <int O, int A>
+__device__ __noinline__ void tc_tail_step(const TailCtx* cx, uint32_t s, uint32_t nsteps, unsigned char* sm, uint64_t* bars) {
+    using P = Packed<O, A>;
+    using S = TcSmem<O, A>;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const struct { long long* dbg; } g = {cx->dbg};      // for the stamp macros
+    (void)g;
+    // ================= in-kernel tail: fold partials, [all-reduce over NVLink peer memory], clip, Adam =================
+    // Only the 512 compute threads take part: named barrier 13, count 512.
+    constexpr uint32_t BAR_TAIL = 13;
+    const TailArgs& tl = cx->tl;
+    const AdamArgs& ad = tl.a;
+    const int PP = ad.P;
+    float neg_step_size = tl.neg_step_size_s[s], bc2_sqrt = tl.bc2_sqrt_s[s];
+    uint32_t seq = tl.seq + s;
+    if (tl.ctrl != nullptr) {        // counters of a graph-replayed update live in device memory
+        neg_step_size = tl.ctrl->neg_step_size[tl.ordinal + s];
+        bc2_sqrt = tl.ctrl->bc2_sqrt[tl.ordinal + s];
+        seq = tl.ctrl->comm_seq + (uint32_t)(tl.ordinal + s) + 1u;
+    }
+    float* const loss_terms_out = tl.loss_terms_out != nullptr ? tl.loss_terms_out + LOSS_TERMS * s : nullptr;
+    const uint32_t bar_target = (s + 1u) * gridDim.x;      // the grid-barrier counters count on through the minibatches of the launch
+    const int nparts = gridDim.x;
+    float* tred = reinterpret_cast<float*>(sm + S::OFF_H1);              // [8][64] fold scratch (tiles are dead now)
+    double* dred = reinterpret_cast<double*>(sm + S::OFF_H1 + 4096);     // [16] warp partials of the squared norm
+    float* sbc = reinterpret_cast<float*>(sm + S::OFF_H1 + 8192);        // broadcast slot
+    // All CTAs are co-resident (cooperative launch).  The CTA's writes are ordered before thread 0's release-increment by the
+    // named barrier (the release is cumulative), the acquire-load orders the other CTAs' writes before everything after the
+    // second named barrier: one thread fences, once per side, instead of a sequentially-consistent fence in all 512.
+    auto grid_barrier = [&](uint32_t* ctr) {
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+        if (tid == 0) {
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+            uint32_t seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+            } while (seen < bar_target);
+        }
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    };
+    grid_barrier(tl.ctr + 0);                     // every CTA's partial gradient is in global memory
+    TC_KSTAMP(6);
+    const int chunk = (PP + nparts - 1) / nparts;
+    const int p_lo = blockIdx.x * chunk, p_hi = min(PP, p_lo + chunk);
+    const int pl = tid & 63, sl = tid >> 6;        // parameter within a group of 64, slice of the partials (8 slices)
+    const bool multi = tl.world > 1;
+    const CommLayout cl = comm_layout(PP);
+    const uint32_t gen = seq & 1u;
+    double sq = 0.0;
+    for (int p0 = p_lo; p0 < p_hi; p0 += 64) {
+        const int p = p0 + pl;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (p < p_hi) {
+            // all (up to 20) loads of this thread in flight at once: one L2 round trip instead of seven.  The summation
+            // keeps the association of grad_reduce_kernel: four interleaved accumulators over groups of 32 partials while a
+            // whole group fits, then the remaining partials one by one into the first accumulator.
+            static_assert(MAX_GRAD_CTAS <= 160, "fold is unrolled for at most 160 partials");
+            float pv[20];
+#pragma unroll
+            for (int j = 0; j < 20; ++j) {
+                const int c = sl + 8 * j;
+                pv[j] = c < nparts ? __ldcg(cx->grad_part + (size_t)c * cx->ppad + p) : 0.0f;
+            }
+            bool rest = false;
+#pragma unroll
+            for (int gq = 0; gq < 5; ++gq) {
+                const int c = sl + 32 * gq;
+                if (!rest && c + 24 < nparts) {
+                    a0 += pv[4 * gq]; a1 += pv[4 * gq + 1]; a2 += pv[4 * gq + 2]; a3 += pv[4 * gq + 3];
+                } else {
+                    rest = true;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (c + 8 * q < nparts) a0 += pv[4 * gq + q];
+                }
+            }
+        }
+        tred[sl * 64 + pl] = (a0 + a1) + (a2 + a3);
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+        if (sl == 0 && p < p_hi) {
+            float t = tred[pl];
+#pragma unroll
+            for (int y = 1; y < 8; ++y) t += tred[y * 64 + pl];
+            if (multi) {
+                // push: this rank's folded value goes into slot `rank` of EVERY rank's symmetric buffer (remote stores over NVLink
+                // are posted; nobody has to fetch it later)
+                for (int rk = 0; rk < tl.world; ++rk)
+                    reinterpret_cast<float*>(tl.peer[rk] + cl.xgrad[gen] + (size_t)tl.rank * cl.rank_stride)[p] = t;
+            } else {
+                tl.grad_out[p] = t;
+                const double gs = (double)(t * ad.grad_scale);
+                sq = fma(gs, gs, sq);
+            }
+        }
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    }
+    TC_KSTAMP(7);
+    if (multi) {
+        // ---- one-shot all-reduce over NVLink, slice by slice: every CTA publishes ITS slice with its own flag in every peer's
+        // buffer as soon as the slice is folded, and waits only for the same slice of the other ranks (no grid-wide barrier) ----
+        if (sl == 0) __threadfence_system();          // the threads that wrote: their remote stores are ordered before the flag
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+        if (tid < tl.world) {
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(tl.peer[tid] + cl.flags[gen] + sizeof(uint32_t) * (tl.rank * FLAG_CTAS + blockIdx.x)) = seq;
+            const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(tl.peer[tl.rank] + cl.flags[gen] +
+                                                                                    sizeof(uint32_t) * (tid * FLAG_CTAS + blockIdx.x));
+            const long long t0 = clock64();
+            while (*f < seq) {
+                if (clock64() - t0 > 40000000000ll) {   // ~20 s: a peer is gone (start-up skew between ranks can reach seconds)
+                    if (tl.error_flag) { *reinterpret_cast<volatile int*>(tl.error_flag) = 1; __threadfence(); }
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
+        named_bar_sync(BAR_TAIL, TC_COMPUTE);
+        const float* mine = reinterpret_cast<const float*>(tl.peer[tl.rank] + cl.xgrad[gen]);
+        for (int p = p_lo + tid; p < p_hi; p += TC_COMPUTE) {
+            float t = 0.0f;
+            for (int rk = 0; rk < tl.world; ++rk)                      // rank order: the same sum on every rank
+                t += __ldcg(mine + (size_t)rk * (cl.rank_stride / sizeof(float)) + p);
+            tl.grad_out[p] = t;
+            const double gs = (double)(t * ad.grad_scale);
+            sq = fma(gs, gs, sq);
+        }
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) dred[warp] = sq;
+    named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    if (tid == 0) {
+        double t = 0.0;
+        for (int wv = 0; wv < TC_COMPUTE / 32; ++wv) t += dred[wv];
+        tl.cta_sumsq[blockIdx.x] = t;
+    }
+    TC_KSTAMP(8);
+    // optimizer state of this thread's first parameter: fetched before the barrier, it does not depend on the norm
+    const int p_first = p_lo + tid;
+    float pre_m = 0.f, pre_v = 0.f, pre_w = 0.f;
+    if (p_first < p_hi) { pre_m = ad.m[p_first]; pre_v = ad.v[p_first]; pre_w = ad.params[p_first]; }
+    grid_barrier(tl.ctr + 2);                     // every CTA's squared-norm share is published
+    TC_KSTAMP(9);
+    if (warp == 0) {
+        double tot = 0.0;
+        for (int i = lane; i < nparts; i += 32) tot += __ldcg(tl.cta_sumsq + i);
+        tot = warp_sum(tot);
+        if (lane == 0) {
+            const float norm = (float)sqrt(tot);
+            const float cf = ad.max_norm / (norm + 1e-6f);
+            sbc[0] = cf < 1.0f ? cf : 1.0f;
+            if (blockIdx.x == 0 && ad.norm_out) *ad.norm_out = norm;
+        }
+    } else if (blockIdx.x == 0 && warp >= 1 && warp <= 5 && loss_terms_out != nullptr) {
+        float t = 0.f;                                    // warp w folds loss term w-1 over the CTAs
+        for (int c = lane; c < nparts; c += 32) t += __ldcg(cx->loss_part + c * LOSS_TERMS + (warp - 1));
+        t = warp_sum(t);
+        if (lane == 0) sbc[4 + warp - 1] = t;
+    }
+    named_bar_sync(BAR_TAIL, TC_COMPUTE);
+    const float coef = sbc[0];
+    // A peer that missed the all-reduce timeout left garbage in the summed gradient: skip the optimizer step on every CTA
+    // (the flag was written before the grid barrier above, so all CTAs agree; it is sticky, the host raises on its next read).
+    const bool peer_lost = multi && tl.error_flag != nullptr && *reinterpret_cast<volatile int*>(tl.error_flag) != 0;
+    for (int p = p_lo + tid; p < p_hi && !peer_lost; p += TC_COMPUTE) {
+        const float gsc = (__ldcg(tl.grad_out + p) * ad.grad_scale) * coef;
+        float m, v, wgt;
+        if (p == p_first) { m = pre_m; v = pre_v; wgt = pre_w; }
+        else { m = ad.m[p]; v = ad.v[p]; wgt = ad.params[p]; }
+        m = m + ad.om_beta1 * (gsc - m);
+        v = v * ad.beta2 + (ad.om_beta2 * gsc) * gsc;
+        const float denom = sqrtf(v) / bc2_sqrt + ad.eps;
+        wgt = wgt + (neg_step_size * m) / denom;
+        ad.m[p] = m; ad.v[p] = v; ad.params[p] = wgt;
+        if (ad.packed != nullptr) packed_store<O, A>(ad.packed, p, wgt);
+    }
+    TC_KSTAMP(10);
+    if (blockIdx.x == 0 && tid == 0 && loss_terms_out != nullptr) {
+        const float inv = 1.0f / (float)cx->mb_count;
+        const float pg = sbc[4] * inv, vl = 0.5f * sbc[5] * inv, en = sbc[6] * inv;
+        loss_terms_out[0] = pg - cx->ent_coef * en + vl * cx->vf_coef;
+        loss_terms_out[1] = pg; loss_terms_out[2] = vl; loss_terms_out[3] = en;
+        loss_terms_out[4] = sbc[7] * inv; loss_terms_out[5] = sbc[8] * inv;
+        loss_terms_out[6] = 0.0f; loss_terms_out[7] = 0.0f;
+    }
+    if (s + 1 < nsteps) {
+        // next minibatch of the launch: every CTA has applied its slice of the Adam step (and refreshed its part of the packed
+        // weights) -> reload the weight tiles; the loader has the first [obs|1] tiles in the ring already
+        grid_barrier(tl.ctr + 1);
+        if (tid == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");      // other CTAs' generic-proxy stores -> this thread's TMA reads
+            mbar_expect_tx(bars, (uint32_t)S::W_BYTES);
+            const char* src = reinterpret_cast<const char*>(cx->packed + P::TC_W2);
+            for (uint32_t off = 0; off < (uint32_t)S::W_BYTES; off += 16384u) {
+                const uint32_t nb = (uint32_t)S::W_BYTES - off < 16384u ? (uint32_t)S::W_BYTES - off : 16384u;
+                bulk_g2s(sm + S::OFF_W + off, src + off, nb, bars);
+            }
+        }
+    } else if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(tl.ctr + 3, 1u) == gridDim.x - 1) { tl.ctr[0] = 0u; tl.ctr[1] = 0u; tl.ctr[2] = 0u; tl.ctr[3] = 0u; }   // re-arm
+    }
+}
+
 template <int O, int A, int OP, int RW>
-__global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs g) {
+__global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(const __grid_constant__ GradArgs g) {
     using P = Packed<O, A>;
     using S = TcSmem<O, A>;
     constexpr int OW = P::OW;
@@ -128,6 +344,12 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         mbar_fence_init();
     }
     if (warp == 1) umma::tmem_alloc(slot, TC_COLS);
+    if (tid == 64 && g.tail.enabled) {       // the tail's arguments -> shared memory (read after the barrier below, by everybody)
+        TailCtx* c = reinterpret_cast<TailCtx*>(sm + S::OFF_CTX);
+        c->tl = g.tail;
+        c->grad_part = g.grad_part; c->loss_part = g.loss_part; c->packed = const_cast<float*>(g.packed); c->dbg = g.dbg;
+        c->ppad = g.ppad; c->mb_count = g.mb_count; c->ent_coef = g.ent_coef; c->vf_coef = g.vf_coef;
+    }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -618,202 +840,7 @@ __global__ void __launch_bounds__(GRAD_TC_BLOCK, 1) ppo_grad_tc_kernel(GradArgs 
         part[i] = stage[src];
     }
     TC_KSTAMP(5);
-    if (g.tail.enabled) {
-    // ================= in-kernel tail: fold partials, [all-reduce over NVLink peer memory], clip, Adam =================
-    // Only the 512 compute threads take part: named barrier 13, count 512.
-    constexpr uint32_t BAR_TAIL = 13;
-    const TailArgs& tl = g.tail;
-    const AdamArgs& ad = tl.a;
-    const int PP = ad.P;
-    float neg_step_size = tl.neg_step_size_s[s], bc2_sqrt = tl.bc2_sqrt_s[s];
-    uint32_t seq = tl.seq + s;
-    if (tl.ctrl != nullptr) {        // counters of a graph-replayed update live in device memory
-        neg_step_size = tl.ctrl->neg_step_size[tl.ordinal + s];
-        bc2_sqrt = tl.ctrl->bc2_sqrt[tl.ordinal + s];
-        seq = tl.ctrl->comm_seq + (uint32_t)(tl.ordinal + s) + 1u;
-    }
-    float* const loss_terms_out = tl.loss_terms_out != nullptr ? tl.loss_terms_out + LOSS_TERMS * s : nullptr;
-    const uint32_t bar_target = (s + 1u) * gridDim.x;      // the grid-barrier counters count on through the minibatches of the launch
-    const int nparts = gridDim.x;
-    float* tred = reinterpret_cast<float*>(sm + S::OFF_H1);              // [8][64] fold scratch (tiles are dead now)
-    double* dred = reinterpret_cast<double*>(sm + S::OFF_H1 + 4096);     // [16] warp partials of the squared norm
-    float* sbc = reinterpret_cast<float*>(sm + S::OFF_H1 + 8192);        // broadcast slot
-    // All CTAs are co-resident (cooperative launch).  The CTA's writes are ordered before thread 0's release-increment by the
-    // named barrier (the release is cumulative), the acquire-load orders the other CTAs' writes before everything after the
-    // second named barrier: one thread fences, once per side, instead of a sequentially-consistent fence in all 512.
-    auto grid_barrier = [&](uint32_t* ctr) {
-        named_bar_sync(BAR_TAIL, TC_COMPUTE);
-        if (tid == 0) {
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-            uint32_t seen;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-            } while (seen < bar_target);
-        }
-        named_bar_sync(BAR_TAIL, TC_COMPUTE);
-    };
-    grid_barrier(tl.ctr + 0);                     // every CTA's partial gradient is in global memory
-    TC_KSTAMP(6);
-    const int chunk = (PP + nparts - 1) / nparts;
-    const int p_lo = blockIdx.x * chunk, p_hi = min(PP, p_lo + chunk);
-    const int pl = tid & 63, sl = tid >> 6;        // parameter within a group of 64, slice of the partials (8 slices)
-    const bool multi = tl.world > 1;
-    const CommLayout cl = comm_layout(PP);
-    const uint32_t gen = seq & 1u;
-    double sq = 0.0;
-    for (int p0 = p_lo; p0 < p_hi; p0 += 64) {
-        const int p = p0 + pl;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        if (p < p_hi) {
-            // all (up to 20) loads of this thread in flight at once: one L2 round trip instead of seven.  The summation
-            // keeps the association of grad_reduce_kernel: four interleaved accumulators over groups of 32 partials while a
-            // whole group fits, then the remaining partials one by one into the first accumulator.
-            static_assert(MAX_GRAD_CTAS <= 160, "fold is unrolled for at most 160 partials");
-            float pv[20];
-#pragma unroll
-            for (int j = 0; j < 20; ++j) {
-                const int c = sl + 8 * j;
-                pv[j] = c < nparts ? __ldcg(g.grad_part + (size_t)c * g.ppad + p) : 0.0f;
-            }
-            bool rest = false;
-#pragma unroll
-            for (int gq = 0; gq < 5; ++gq) {
-                const int c = sl + 32 * gq;
-                if (!rest && c + 24 < nparts) {
-                    a0 += pv[4 * gq]; a1 += pv[4 * gq + 1]; a2 += pv[4 * gq + 2]; a3 += pv[4 * gq + 3];
-                } else {
-                    rest = true;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (c + 8 * q < nparts) a0 += pv[4 * gq + q];
-                }
-            }
-        }
-        tred[sl * 64 + pl] = (a0 + a1) + (a2 + a3);
-        named_bar_sync(BAR_TAIL, TC_COMPUTE);
-        if (sl == 0 && p < p_hi) {
-            float t = tred[pl];
-#pragma unroll
-            for (int y = 1; y < 8; ++y) t += tred[y * 64 + pl];
-            if (multi) {
-                // push: this rank's folded value goes into slot `rank` of EVERY rank's symmetric buffer (remote stores over NVLink
-                // are posted; nobody has to fetch it later)
-                for (int rk = 0; rk < tl.world; ++rk)
-                    reinterpret_cast<float*>(tl.peer[rk] + cl.xgrad[gen] + (size_t)tl.rank * cl.rank_stride)[p] = t;
-            } else {
-                tl.grad_out[p] = t;
-                const double gs = (double)(t * ad.grad_scale);
-                sq = fma(gs, gs, sq);
-            }
-        }
-        named_bar_sync(BAR_TAIL, TC_COMPUTE);
-    }
-    TC_KSTAMP(7);
-    if (multi) {
-        // ---- one-shot all-reduce over NVLink, slice by slice: every CTA publishes ITS slice with its own flag in every peer's
-        // buffer as soon as the slice is folded, and waits only for the same slice of the other ranks (no grid-wide barrier) ----
-        if (sl == 0) __threadfence_system();          // the threads that wrote: their remote stores are ordered before the flag
-        named_bar_sync(BAR_TAIL, TC_COMPUTE);
-        if (tid < tl.world) {
-            __threadfence_system();
-            *reinterpret_cast<volatile uint32_t*>(tl.peer[tid] + cl.flags[gen] + sizeof(uint32_t) * (tl.rank * FLAG_CTAS + blockIdx.x)) = seq;
-            const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(tl.peer[tl.rank] + cl.flags[gen] +
-                                                                                    sizeof(uint32_t) * (tid * FLAG_CTAS + blockIdx.x));
-            const long long t0 = clock64();
-            while (*f < seq) {
-                if (clock64() - t0 > 40000000000ll) {   // ~20 s: a peer is gone (start-up skew between ranks can reach seconds)
-                    if (tl.error_flag) { *reinterpret_cast<volatile int*>(tl.error_flag) = 1; __threadfence(); }
-                    break;
-                }
-            }
-            __threadfence_system();
-        }
-        named_bar_sync(BAR_TAIL, TC_COMPUTE);
-        const float* mine = reinterpret_cast<const float*>(tl.peer[tl.rank] + cl.xgrad[gen]);
-        for (int p = p_lo + tid; p < p_hi; p += TC_COMPUTE) {
-            float t = 0.0f;
-            for (int rk = 0; rk < tl.world; ++rk)                      // rank order: the same sum on every rank
-                t += __ldcg(mine + (size_t)rk * (cl.rank_stride / sizeof(float)) + p);
-            tl.grad_out[p] = t;
-            const double gs = (double)(t * ad.grad_scale);
-            sq = fma(gs, gs, sq);
-        }
-    }
-    sq = warp_sum(sq);
-    if (lane == 0) dred[warp] = sq;
-    named_bar_sync(BAR_TAIL, TC_COMPUTE);
-    if (tid == 0) {
-        double t = 0.0;
-        for (int wv = 0; wv < TC_COMPUTE / 32; ++wv) t += dred[wv];
-        tl.cta_sumsq[blockIdx.x] = t;
-    }
-    TC_KSTAMP(8);
-    // optimizer state of this thread's first parameter: fetched before the barrier, it does not depend on the norm
-    const int p_first = p_lo + tid;
-    float pre_m = 0.f, pre_v = 0.f, pre_w = 0.f;
-    if (p_first < p_hi) { pre_m = ad.m[p_first]; pre_v = ad.v[p_first]; pre_w = ad.params[p_first]; }
-    grid_barrier(tl.ctr + 2);                     // every CTA's squared-norm share is published
-    TC_KSTAMP(9);
-    if (warp == 0) {
-        double tot = 0.0;
-        for (int i = lane; i < nparts; i += 32) tot += __ldcg(tl.cta_sumsq + i);
-        tot = warp_sum(tot);
-        if (lane == 0) {
-            const float norm = (float)sqrt(tot);
-            const float cf = ad.max_norm / (norm + 1e-6f);
-            sbc[0] = cf < 1.0f ? cf : 1.0f;
-            if (blockIdx.x == 0 && ad.norm_out) *ad.norm_out = norm;
-        }
-    } else if (blockIdx.x == 0 && warp >= 1 && warp <= 5 && loss_terms_out != nullptr) {
-        float t = 0.f;                                    // warp w folds loss term w-1 over the CTAs
-        for (int c = lane; c < nparts; c += 32) t += __ldcg(g.loss_part + c * LOSS_TERMS + (warp - 1));
-        t = warp_sum(t);
-        if (lane == 0) sbc[4 + warp - 1] = t;
-    }
-    named_bar_sync(BAR_TAIL, TC_COMPUTE);
-    const float coef = sbc[0];
-    // A peer that missed the all-reduce timeout left garbage in the summed gradient: skip the optimizer step on every CTA
-    // (the flag was written before the grid barrier above, so all CTAs agree; it is sticky, the host raises on its next read).
-    const bool peer_lost = multi && tl.error_flag != nullptr && *reinterpret_cast<volatile int*>(tl.error_flag) != 0;
-    for (int p = p_lo + tid; p < p_hi && !peer_lost; p += TC_COMPUTE) {
-        const float gsc = (__ldcg(tl.grad_out + p) * ad.grad_scale) * coef;
-        float m, v, wgt;
-        if (p == p_first) { m = pre_m; v = pre_v; wgt = pre_w; }
-        else { m = ad.m[p]; v = ad.v[p]; wgt = ad.params[p]; }
-        m = m + ad.om_beta1 * (gsc - m);
-        v = v * ad.beta2 + (ad.om_beta2 * gsc) * gsc;
-        const float denom = sqrtf(v) / bc2_sqrt + ad.eps;
-        wgt = wgt + (neg_step_size * m) / denom;
-        ad.m[p] = m; ad.v[p] = v; ad.params[p] = wgt;
-        if (ad.packed != nullptr) packed_store<O, A>(ad.packed, p, wgt);
-    }
-    TC_KSTAMP(10);
-    if (blockIdx.x == 0 && tid == 0 && loss_terms_out != nullptr) {
-        const float inv = 1.0f / (float)g.mb_count;
-        const float pg = sbc[4] * inv, vl = 0.5f * sbc[5] * inv, en = sbc[6] * inv;
-        loss_terms_out[0] = pg - g.ent_coef * en + vl * g.vf_coef;
-        loss_terms_out[1] = pg; loss_terms_out[2] = vl; loss_terms_out[3] = en;
-        loss_terms_out[4] = sbc[7] * inv; loss_terms_out[5] = sbc[8] * inv;
-        loss_terms_out[6] = 0.0f; loss_terms_out[7] = 0.0f;
-    }
-    if (s + 1 < nsteps) {
-        // next minibatch of the launch: every CTA has applied its slice of the Adam step (and refreshed its part of the packed
-        // weights) -> reload the weight tiles; the loader has the first [obs|1] tiles in the ring already
-        grid_barrier(tl.ctr + 1);
-        if (tid == 0) {
-            asm volatile("fence.proxy.async;" ::: "memory");      // other CTAs' generic-proxy stores -> this thread's TMA reads
-            mbar_expect_tx(bars, (uint32_t)S::W_BYTES);
-            const char* src = reinterpret_cast<const char*>(g.packed + P::TC_W2);
-            for (uint32_t off = 0; off < (uint32_t)S::W_BYTES; off += 16384u) {
-                const uint32_t nb = (uint32_t)S::W_BYTES - off < 16384u ? (uint32_t)S::W_BYTES - off : 16384u;
-                bulk_g2s(sm + S::OFF_W + off, src + off, nb, bars);
-            }
-        }
-    } else if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(tl.ctr + 3, 1u) == gridDim.x - 1) { tl.ctr[0] = 0u; tl.ctr[1] = 0u; tl.ctr[2] = 0u; tl.ctr[3] = 0u; }   // re-arm
-    }
-    }   // tail
+    if (g.tail.enabled) tc_tail_step<O, A>(reinterpret_cast<const TailCtx*>(sm + S::OFF_CTX), s, nsteps, sm, bars);
     }   // minibatches of the launch
     umma::fence_before_sync();
     __syncthreads();           // end of the kernel: with the issuer and the loader warp
